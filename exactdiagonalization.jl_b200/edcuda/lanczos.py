@@ -1,0 +1,182 @@
+"""Lanczos drivers on top of the engine's device kernels.
+
+The reference has no eigensolver of its own (it passes `mul!` to Arpack, docs/src/examples/spinhalf.md:26);
+north_star asks for a device-resident Lanczos whose matvec is the engine's apply and whose dot products are
+NCCL all-reduces when the basis is row-sharded.
+
+  lanczos(opr, n_steps, ...)            one GPU, the whole loop inside libedcuda (ed_lanczos)
+  ShardedLanczos(opr_shard, ...)        one process per GPU: rows [lo, hi) per rank; every step
+                                        all-gathers the Krylov vector (NCCL over NVLink through
+                                        torch.distributed) and all-reduces the two scalars.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from ._lib import ED_C128, ED_F64, ED_SIDE_LEFT, check, lib
+
+
+@dataclass
+class LanczosResult:
+    alpha: np.ndarray
+    beta: np.ndarray
+    ritz: np.ndarray
+    steps: int
+
+
+def tridiag_eigvals(alpha, beta) -> np.ndarray:
+    a = np.ascontiguousarray(alpha, dtype=np.float64)
+    b = np.ascontiguousarray(beta, dtype=np.float64)
+    out = np.empty(len(a), dtype=np.float64)
+    if len(a):
+        check(lib.ed_tridiag_eigvals(a.ctypes.data, b.ctypes.data if len(b) else None, len(a), out.ctypes.data))
+    return out
+
+
+def lanczos(opr, n_steps: int, v0: Optional[np.ndarray] = None, seed: int = 0, dtype=None, n_ritz: int = 4) -> LanczosResult:
+    """Single-GPU Lanczos: `n_steps` steps from `v0` (numpy, host) or from a Philox-seeded normal vector."""
+    if dtype is None:
+        dtype = np.complex128 if (opr.is_complex or (v0 is not None and np.iscomplexobj(v0))) else np.float64
+    code = ED_C128 if np.dtype(dtype) == np.complex128 else ED_F64
+    ptr = None
+    if v0 is not None:
+        v0 = np.ascontiguousarray(v0, dtype=dtype)
+        if v0.size != opr.dimension:
+            from ._lib import DimensionMismatch
+            raise DimensionMismatch("start vector length differs from the dimension")
+        ptr = v0.ctypes.data
+    alpha = np.zeros(n_steps)
+    beta = np.zeros(n_steps)
+    n_ritz = min(n_ritz, n_steps)
+    ritz = np.zeros(n_ritz)
+    done = C.c_int32()
+    check(lib.ed_lanczos(opr._handle, n_steps, ptr, code, seed, alpha.ctypes.data, beta.ctypes.data, ritz.ctypes.data,
+                         n_ritz, C.byref(done)))
+    k = done.value
+    return LanczosResult(alpha[:k], beta[:k], ritz[: min(n_ritz, k)], k)
+
+
+def split_rows(dim: int, world: int):
+    """Contiguous, count-balanced row ranges (the reference's splitrange, src/util.jl:102-121)."""
+    base, rem = divmod(dim, world)
+    sizes = [base + (1 if r < rem else 0) for r in range(world)]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    return [(int(offs[r]), int(offs[r + 1])) for r in range(world)]
+
+
+class ShardedMatvec:
+    """Row-sharded y = H x over torch.distributed: x shards are all-gathered (NCCL over NVLink on GPUs),
+    then every rank applies its rows.  `opr` is this rank's representation (set_rows is called here)."""
+
+    def __init__(self, opr, rank: int, world: int, dtype=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.opr, self.rank, self.world, self.group = opr, rank, world, group
+        self.dim = opr.dimension
+        self.ranges = split_rows(self.dim, world)
+        self.lo, self.hi = self.ranges[rank]
+        opr.set_rows(self.lo, self.hi)
+        self.np_dtype = np.dtype(dtype or (np.complex128 if opr.is_complex else np.float64))
+        self.t_dtype = torch.complex128 if self.np_dtype == np.complex128 else torch.float64
+        self.code = ED_C128 if self.np_dtype == np.complex128 else ED_F64
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.max_rows = max(h - l for l, h in self.ranges)
+        self.uniform = all(h - l == self.max_rows for l, h in self.ranges)
+        # full-length gather target; with ragged shards every rank pads to max_rows and the pieces are compacted
+        self.x_full = torch.zeros(self.dim, dtype=self.t_dtype, device=self.dev)
+        if not self.uniform:
+            self.x_pad = torch.zeros(self.max_rows * world, dtype=self.t_dtype, device=self.dev)
+            self.send = torch.zeros(self.max_rows, dtype=self.t_dtype, device=self.dev)
+
+    def gather(self, x_local):
+        """all-gather the rank-local rows into the full-length vector."""
+        dist = self.dist
+        if self.world == 1:
+            self.x_full.copy_(x_local)
+        elif self.uniform:
+            dist.all_gather_into_tensor(self.x_full, x_local, group=self.group)
+        else:
+            self.send[: self.hi - self.lo].copy_(x_local)
+            dist.all_gather_into_tensor(self.x_pad, self.send, group=self.group)
+            for r, (l, h) in enumerate(self.ranges):
+                self.x_full[l:h].copy_(self.x_pad[r * self.max_rows: r * self.max_rows + (h - l)])
+        return self.x_full
+
+    def apply_local(self, y_local, x_full, dot_out=None):
+        torch = self.torch
+        check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+        try:
+            check(lib.ed_apply_async(self.opr._handle, y_local.data_ptr(), x_full.data_ptr(), self.code, ED_SIDE_LEFT, 0,
+                                     dot_out.data_ptr() if dot_out is not None else None))
+        finally:
+            lib.ed_set_stream(None, 0)
+        return y_local
+
+    def matvec(self, y_local, x_local, dot_out=None):
+        return self.apply_local(y_local, self.gather(x_local), dot_out)
+
+
+class ShardedLanczos:
+    """Three-term Lanczos with unnormalised, device-resident, row-sharded Krylov vectors (see csrc/lanczos.cu).
+    Per step: one all-gather (x), two scalar all-reduces (<u,Hu> and |u_next|^2); no host synchronisation."""
+
+    def __init__(self, opr, rank: int = 0, world: int = 1, dtype=None, group=None):
+        self.mv = ShardedMatvec(opr, rank, world, dtype, group)
+        torch = self.mv.torch
+        n = self.mv.hi - self.mv.lo
+        self.n_local = n
+        mk = lambda: torch.zeros(max(n, 1), dtype=self.mv.t_dtype, device=self.mv.dev)[:n]
+        self.u_cur, self.u_prev, self.w = mk(), mk(), mk()
+
+    def _ed_stream(self):
+        torch = self.mv.torch
+        check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+
+    def run(self, n_steps: int, seed: int = 0, v0_local=None, n_ritz: int = 4) -> LanczosResult:
+        mv, torch, dist = self.mv, self.mv.torch, self.mv.dist
+        dots = torch.zeros(n_steps, 2, dtype=torch.float64, device=mv.dev)
+        norms = torch.zeros(n_steps + 1, 2, dtype=torch.float64, device=mv.dev)
+        self.u_prev.zero_()
+        self._ed_stream()
+        try:
+            if v0_local is not None:
+                self.u_cur.copy_(v0_local)
+            else:
+                check(lib.ed_vector_randn_async(self.u_cur.data_ptr(), self.n_local, mv.code, seed, mv.lo))
+            check(lib.ed_vector_norm2_async(self.u_cur.data_ptr(), self.n_local, mv.code, norms[0].data_ptr()))
+        finally:
+            lib.ed_set_stream(None, 0)
+        if mv.world > 1:
+            dist.all_reduce(norms[0], group=mv.group)
+        for j in range(n_steps):
+            mv.matvec(self.w, self.u_cur, dots[j])
+            if mv.world > 1:
+                dist.all_reduce(dots[j], group=mv.group)
+            self._ed_stream()
+            try:
+                check(lib.ed_lanczos_update_async(self.u_prev.data_ptr(), self.w.data_ptr(), self.u_cur.data_ptr(), self.n_local,
+                                                  mv.code, dots[j].data_ptr(), norms[j].data_ptr(),
+                                                  norms[j - 1].data_ptr() if j > 0 else None, norms[j + 1].data_ptr()))
+            finally:
+                lib.ed_set_stream(None, 0)
+            if mv.world > 1:
+                dist.all_reduce(norms[j + 1], group=mv.group)
+            self.u_cur, self.u_prev = self.u_prev, self.u_cur
+        torch.cuda.synchronize()
+        hd, hn = dots.cpu().numpy(), norms.cpu().numpy()
+        alpha, beta = [], []
+        for j in range(n_steps):
+            if not (hn[j, 0] > 0.0) or not np.isfinite(hn[j, 0]):
+                break
+            alpha.append(hd[j, 0] / hn[j, 0])
+            beta.append(float(np.sqrt(hn[j + 1, 0])))
+            if not (beta[-1] > 1e-13 * abs(alpha[-1]) + 1e-300):
+                break
+        alpha, beta = np.array(alpha), np.array(beta)
+        ritz = tridiag_eigvals(alpha, beta[:-1] if len(beta) else beta)[:n_ritz] if len(alpha) else np.array([])
+        return LanczosResult(alpha, beta, ritz, len(alpha))

@@ -1,0 +1,235 @@
+/*
+ * edcuda.h -- C ABI of libedcuda.so, the B200 (sm_100a) engine behind
+ * ExactDiagonalization.jl's Hamiltonian-application path.
+ *
+ * The reference (v0.14.3, /root/reference) has no FFI of its own: its boundary is the
+ * Julia method surface.  Each entry point below names the reference method(s) it
+ * replaces (file:line under /root/reference/src).  The Julia shim that binds them by
+ * `ccall` is exactdiagonalization.jl_b200/julia/EDCuda.jl; the Python mirror used by
+ * the tests is exactdiagonalization.jl_b200/edcuda/.
+ *
+ * Conventions
+ *   - every call returns an int status (ED_OK == 0); ed_last_error() gives the message
+ *     of the calling thread's last failure.  Status codes map the reference's exception
+ *     types one-to-one (ArgumentError, DimensionMismatch, BoundsError, KeyError).
+ *   - indices crossing the ABI are 1-based Int64 exactly as in the reference
+ *     (-1 = "not in the basis"); basis words are uint64 (BR = UInt64 storage; the
+ *     `br_bits` argument only reproduces the reference's width check).
+ *   - vectors are Float64 (ED_F64) or ComplexF64 (ED_C128, interleaved re,im).
+ *   - `void*` vector arguments may be HOST or DEVICE pointers; the library detects which
+ *     (cudaPointerGetAttributes).  Host buffers are staged through device memory inside
+ *     the call; device buffers are used in place on the library's stream.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ *     with ED_ERR_CUDA.
+ *   - handles are opaque, created by *_create / *_generate / *_reduce and released by the
+ *     matching *_destroy.  A handle keeps what it needs from its inputs alive itself.
+ *   - one in-flight call per handle; calls are stream-ordered on the library stream
+ *     (ed_set_stream) and synchronise before returning unless stated otherwise.
+ */
+#ifndef EDCUDA_H
+#define EDCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------ */
+#define ED_OK                     0
+#define ED_ERR_ARGUMENT           1  /* Julia ArgumentError     */
+#define ED_ERR_DIMENSION_MISMATCH 2  /* Julia DimensionMismatch */
+#define ED_ERR_BOUNDS             3  /* Julia BoundsError       */
+#define ED_ERR_KEY                4  /* Julia KeyError          */
+#define ED_ERR_CUDA               5  /* CUDA runtime failure / no device */
+#define ED_ERR_UNSUPPORTED        6  /* valid in the reference, outside this engine (e.g. BR wider than 64 bit) */
+#define ED_ERR_INTERNAL           7
+
+/* ---- scalar types / flags ---------------------------------------------------------- */
+#define ED_F64   0
+#define ED_C128  1
+
+#define ED_SIDE_LEFT  0  /* out (+)= H * x   : row walk,    apply!(out, opr, state) */
+#define ED_SIDE_RIGHT 1  /* out (+)= x * H   : column walk, apply!(out, state, opr) */
+
+/* how a basis answers "word -> index" */
+#define ED_BASIS_LIST        0  /* sorted array + binary search  (FrozenSortedArrayIndex) */
+#define ED_BASIS_FULL        1  /* whole space, every site a power of two: index = word    */
+#define ED_BASIS_COMBINADIC  2  /* 1-bit sites, one U(1) value: combinatorial number system */
+#define ED_BASIS_DPRANK      3  /* any HilbertSpaceSector: per-site DP rank tables          */
+
+typedef struct ed_space    ed_space;
+typedef struct ed_basis    ed_basis;
+typedef struct ed_operator ed_operator;
+typedef struct ed_symmetry ed_symmetry;
+typedef struct ed_rbasis   ed_rbasis;
+typedef struct ed_oprep    ed_oprep;
+
+/* ---- library ----------------------------------------------------------------------- */
+const char* ed_last_error(void);
+const char* ed_version(void);
+/* number of CUDA devices visible (0 when none: every compute call will fail). */
+int  ed_device_count(void);
+/* select the device used by the calling thread's subsequent calls (cudaSetDevice). */
+int  ed_set_device(int device);
+/* enable != 0: run this thread's library work on `cuda_stream` (a cudaStream_t; NULL = the legacy default
+ * stream) instead of the library's own non-blocking stream; enable == 0 restores the library stream. */
+int  ed_set_stream(void* cuda_stream, int32_t enable);
+/* total number of kernel launches issued by the library in this process (for bench accounting). */
+int64_t ed_kernel_launch_count(void);
+
+/* ---- HilbertSpace  (HilbertSpace/hilbert_space.jl:25-41, site.jl:69-93) ------------- */
+/* n_states[i] local states on site i; qn is [sum_i n_states[i]][n_qn] row-major: the quantum
+ * number tuple of every local state in site order.  Site 0 occupies the least significant
+ * bits; width(site) = ceil(log2(n_states)). */
+int ed_space_create(int32_t n_sites, const int32_t* n_states, const int64_t* qn, int32_t n_qn,
+                    ed_space** out);
+int ed_space_destroy(ed_space* space);
+int ed_space_bitwidth(const ed_space* space, int32_t* bitwidth);   /* hilbert_space.jl:96 */
+
+/* ---- HilbertSpaceRepresentation  (Representation/hilbert_space_representation.jl) -- */
+/* represent(hs, BR) / represent(HilbertSpaceSector(hs, allowed), BR)   :215-230, basis :109-206.
+ * allowed_qn is [n_allowed][n_qn]; n_allowed < 0 means "whole space" (represent(hs)).
+ * Allowed values that the space cannot reach are ignored (hilbert_space_sector.jl:27-63).
+ * br_bits = 8*sizeof(BR) of the caller: ArgumentError when br_bits <= bitwidth (:63-69, :110, :129);
+ * br_bits > 64 -> ED_ERR_UNSUPPORTED.  The basis is generated ON DEVICE, ascending. */
+int ed_basis_generate(const ed_space* space, const int64_t* allowed_qn, int64_t n_allowed,
+                      int32_t br_bits, ed_basis** out);
+/* represent(hs, basis_list) :242-256 -- sorts if unsorted; duplicates -> ED_ERR_ARGUMENT
+ * (frozensortedarray.jl:15-19). words is a host pointer. */
+int ed_basis_from_list(const ed_space* space, const uint64_t* words, int64_t n, int32_t br_bits,
+                       ed_basis** out);
+int ed_basis_destroy(ed_basis* basis);
+int ed_basis_dim(const ed_basis* basis, int64_t* dim);              /* dimension() :90 */
+int ed_basis_kind(const ed_basis* basis, int32_t* kind);
+/* copy basis_list[lo+1 .. lo+n] (0-based offset lo) to a host buffer. */
+int ed_basis_download(ed_basis* basis, int64_t lo, int64_t n, uint64_t* words_out);
+/* get(basis_lookup, key, -1) for n host keys (frozensortedarray.jl:29-48): 1-based index or -1. */
+int ed_basis_lookup(ed_basis* basis, const uint64_t* keys, int64_t n, int64_t* index_out);
+/* device pointer to the (materialised) ascending word array, for zero-copy consumers. */
+int ed_basis_device_words(ed_basis* basis, const uint64_t** dev_words);
+
+/* ---- SumOperator  (Operator/pure_operator.jl:25-52, sum_operator.jl:13-23) ---------- */
+/* terms in the reference's order; amplitude is n_terms doubles, or n_terms (re,im) pairs when
+ * is_complex.  ArgumentError if bitrow/bitcol has a bit outside bitmask (pure_operator.jl:32-36). */
+int ed_operator_create(int64_t n_terms, const uint64_t* bitmask, const uint64_t* bitrow,
+                       const uint64_t* bitcol, const double* amplitude, int32_t is_complex,
+                       ed_operator** out);
+int ed_operator_destroy(ed_operator* op);
+
+/* ---- symmetry  (Symmetry/symmetry_apply.jl:65-92, bitflipsymmetry.jl:23-35) --------- */
+/* n_ops group elements; perm[g*n_sites + i] = j sends site i to site j (0-based; the
+ * SitePermutation.permutation.map of the reference minus one).  flip[g] != 0 composes the
+ * element with GlobalBitFlip(true) (NULL = none).  chi[2g], chi[2g+1] = (re, im) of the
+ * amplitude handed to symmetry_reduce(hsr, symops_and_amplitudes).  Element 0 must be the
+ * identity (symmetry_reduce_generic.jl:56).  ArgumentError unless every |chi| ~ 1 (:27-29). */
+int ed_symmetry_create(int32_t n_ops, int32_t n_sites, const int32_t* perm, const uint8_t* flip,
+                       const double* chi, ed_symmetry** out);
+int ed_symmetry_destroy(ed_symmetry* sym);
+/* symmetry_apply(hs, op_g, word) for n host words: images_out[k] = g(words[k]). */
+int ed_symmetry_apply(const ed_space* space, const ed_symmetry* sym, int32_t g,
+                      const uint64_t* words, int64_t n, uint64_t* images_out);
+
+/* ---- ReducedHilbertSpaceRepresentation  (Symmetry/symmetry_reduce_generic.jl:22-255) */
+/* symmetry_reduce(hsr, symops_and_amplitudes; tol).  Representatives (orbit minima whose
+ * stabiliser characters are ~1 within tol) are filtered and compacted on device without
+ * the per-parent-state arrays of the reference; those are served on demand below. */
+int ed_symmetry_reduce(ed_basis* parent, const ed_symmetry* sym, double tol, ed_rbasis** out);
+int ed_rbasis_destroy(ed_rbasis* rbasis);
+int ed_rbasis_dim(const ed_rbasis* rbasis, int64_t* dim);
+int ed_rbasis_download(ed_rbasis* rbasis, int64_t lo, int64_t n, uint64_t* words_out);
+/* orbit sizes N_r (number of distinct images) of representatives lo .. lo+n-1. */
+int ed_rbasis_orbit_sizes(ed_rbasis* rbasis, int64_t lo, int64_t n, int32_t* sizes_out);
+/* (basis_mapping_index, basis_mapping_amplitude) of n parent WORDS (host):
+ * index 1-based or -1; amplitude (re,im) = conj(chi_g)/sqrt(N_r) with word = g(r), last g wins
+ * (symmetry_reduce_generic.jl:74-101).  Words outside the parent basis give -1. */
+int ed_rbasis_mapping(ed_rbasis* rbasis, const uint64_t* parent_words, int64_t n,
+                      int64_t* index_out, double* amplitude_out);
+/* the reference's two length-dim(parent) arrays for parent rows lo .. lo+n-1. */
+int ed_rbasis_mapping_rows(ed_rbasis* rbasis, int64_t lo, int64_t n,
+                           int64_t* index_out, double* amplitude_out);
+/* symmetry_reduce(rhsr, large_vector) / symmetry_reduce!(out, ...)  (symmetry_reduce.jl:38-153):
+ * small[idx[p]] += conj(amp[p]) * large[p].  accumulate=0 zero-fills first.  small is ED_C128;
+ * large has dtype `large_dtype`.  Lengths are checked -> ED_ERR_DIMENSION_MISMATCH. */
+int ed_vector_reduce(ed_rbasis* rbasis, void* small_out, int64_t n_small, const void* large,
+                     int64_t n_large, int32_t large_dtype, int32_t accumulate);
+/* symmetry_unreduce(rhsr, small_vector)  (symmetry_reduce.jl:208-225): large[p] = amp[p]*small[idx[p]]. */
+int ed_vector_unreduce(ed_rbasis* rbasis, void* large_out, int64_t n_large, const void* small,
+                       int64_t n_small, int32_t small_dtype);
+
+/* ---- OperatorRepresentation / ReducedOperatorRepresentation ------------------------- */
+/* represent(hsr, op)  (Representation/operator_representation.jl:34-36) */
+int ed_oprep_create(ed_basis* basis, const ed_operator* op, ed_oprep** out);
+/* represent(rhsr, op) (Symmetry/reduced_operator_representation.jl:40-42); scalar type is always ComplexF64 (:26) */
+int ed_oprep_create_reduced(ed_rbasis* rbasis, const ed_operator* op, ed_oprep** out);
+int ed_oprep_destroy(ed_oprep* oprep);
+int ed_oprep_dim(const ed_oprep* oprep, int64_t* dim);
+/* ED_F64 or ED_C128: valtype of the representation (complex operator or reduced space -> ED_C128). */
+int ed_oprep_dtype(const ed_oprep* oprep, int32_t* dtype);
+/* Row-shard the representation (multi-GPU): this process owns output rows [row_lo, row_hi)
+ * (0-based, half open).  x keeps the full length; out has row_hi-row_lo elements. Default: all rows. */
+int ed_oprep_set_rows(ed_oprep* oprep, int64_t row_lo, int64_t row_hi);
+/* Choose the kernel: 0 = automatic (fastest exact path), 1 = force the generic term-walk kernel. */
+int ed_oprep_set_kernel(ed_oprep* oprep, int32_t which);
+
+/* apply!(out, opr, x) / apply!(out, x, opr) / mul!(out, opr, x)
+ * (Representation/abstract_operator_representation.jl:110-118, 260-409):
+ *   accumulate=1: out += H*x (apply!);  accumulate=0: out = H*x (mul!).
+ *   n_out / n_x are the callers' vector lengths: checked against the dimension
+ *   (n_out against the owned row count) -> ED_ERR_DIMENSION_MISMATCH (:303-307).
+ *   dtype is the element type of BOTH out and x; a complex representation needs ED_C128. */
+int ed_apply(ed_oprep* oprep, void* out, int64_t n_out, const void* x, int64_t n_x,
+             int32_t dtype, int32_t side, int32_t accumulate);
+/* same, device pointers only, asynchronous on the library stream (no sync before return);
+ * `alpha_dot` (device double[2] or NULL) receives sum_i conj(x[row_i]) * out[i] over the owned rows
+ * (the Lanczos alpha partial, fused in the epilogue). */
+int ed_apply_async(ed_oprep* oprep, void* out, const void* x, int32_t dtype, int32_t side,
+                   int32_t accumulate, double* alpha_dot);
+
+/* get_row_iterator(opr, i) / get_column_iterator(opr, i) (operator_representation.jl:66-103,
+ * reduced_operator_representation.jl:57-116): up to `cap` (index, amplitude) pairs in term
+ * order, misses as -1; *n_out = number of pairs.  i is 1-based; BoundsError outside 1..dim.
+ * amplitude_out holds (re,im) pairs when the representation is complex, else doubles. */
+int ed_oprep_row_iterator(ed_oprep* oprep, int64_t i, int32_t side, int64_t cap,
+                          int64_t* index_out, double* amplitude_out, int64_t* n_out);
+/* get_element(opr, i, j) (operator_representation.jl:109-119, reduced :120-138). value_out = (re, im). */
+int ed_oprep_get_element(ed_oprep* oprep, int64_t i, int64_t j, double* value_out);
+
+/* sparse(opr; tol) (abstract_operator_representation.jl:136-204, util.jl:88-94):
+ * CSC, 1-based Int64 colptr/rowval, rows ascending inside a column, entries with |v| < tol removed.
+ * Two calls: ed_sparse_count assembles on device and returns nnz; ed_sparse_fetch copies the three
+ * arrays (colptr has dim+1 entries; nzval is nnz doubles or nnz (re,im) pairs) and frees the
+ * device copy.  tol < 0 selects the reference default sqrt(eps(Float64)). */
+int ed_sparse_count(ed_oprep* oprep, double tol, int64_t* nnz_out);
+int ed_sparse_fetch(ed_oprep* oprep, int64_t* colptr, int64_t* rowval, void* nzval);
+/* Matrix(opr) (:121-132): dense column-major dim x dim, no chop.  out is a host buffer of the
+ * representation's dtype. */
+int ed_dense(ed_oprep* oprep, void* out);
+
+/* ---- Lanczos driver (not in the reference: it hands mul! to Arpack, docs/src/examples/spinhalf.md:26) */
+/* n_steps of three-term Lanczos on device from v0 (host or device, dim elements of `dtype`; NULL =
+ * Philox-seeded normal vector from `seed`).  alpha[n_steps], beta[n_steps] (host) receive the
+ * tridiagonal; ritz[n_ritz] the lowest Ritz values.  Single device; the sharded multi-GPU loop
+ * lives in the host layer and uses the ed_lanczos_* kernels below with NCCL collectives between them.
+ * steps_done (may be NULL) = number of valid (alpha, beta) pairs (smaller than n_steps on breakdown). */
+int ed_lanczos(ed_oprep* oprep, int32_t n_steps, const void* v0, int32_t dtype, uint64_t seed,
+               double* alpha, double* beta, double* ritz, int32_t n_ritz, int32_t* steps_done);
+/* fused vector update on the owned rows (device pointers, async).  Krylov vectors are kept unnormalised:
+ *   u_next = (w - alpha * u_cur) / n_cur - (n_cur / n_prev) * u_prev ,  alpha = dot[0] / n_cur^2,
+ * written over u_prev;  norm2_out[0] (device double[2]) = sum |u_next|^2 over the owned rows.
+ * dot = device double[2] from ed_apply_async (already summed over shards), norm2_cur / norm2_prev = device
+ * doubles holding |u_cur|^2 and |u_prev|^2 (norm2_prev NULL on the first step). */
+int ed_lanczos_update_async(void* u_prev_inout, const void* w, const void* u_cur, int64_t n, int32_t dtype,
+                            const double* dot, const double* norm2_cur, const double* norm2_prev,
+                            double* norm2_out);
+/* norm2_out[0] (device double[2]) = sum |v|^2 over n elements (async). */
+int ed_vector_norm2_async(const void* v, int64_t n, int32_t dtype, double* norm2_out);
+/* v[i] = normal(0,1) from Philox keyed by (seed, global_row_offset + i): shard-count independent. */
+int ed_vector_randn_async(void* v, int64_t n, int32_t dtype, uint64_t seed, int64_t global_row_offset);
+/* lowest eigenvalues of the k x k symmetric tridiagonal (alpha, beta[0..k-2]) -- host helper. */
+int ed_tridiag_eigvals(const double* alpha, const double* beta, int32_t k, double* eig_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDCUDA_H */

@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- H*v matvec throughput of the engine on the BASELINE.json headline workload.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+Workload (N=1 default): XXZ chain L=32, Sz=0 sector (601,080,390 states, 192 terms) -- the configuration
+BASELINE.json's metric is quoted on; one "step" = one matrix-free matvec y = H x over the whole basis.
+N>1: the same problem row-sharded over N ranks (strong scaling): every step all-gathers x over NCCL and applies
+the local rows.  Prints ONE JSON line (rank 0).  `--impl reference` times the reference algorithm's CPU
+restatement (oracle/ed_oracle_c.c, OpenMP, all host threads) on a bounded row sample of the same workload.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
+
+WORKLOADS = {
+    # name: (n_sites, builder, description)
+    "xxz_chain_L32_sz0": dict(n=32, kind="xxz", desc="XXZ chain L=32 (Delta=1), Sz=0, periodic, Pauli normalisation"),
+    "j1j2_chain_L28_sz0": dict(n=28, kind="j1j2", desc="J1-J2 chain L=28 (J2=0.5), Sz=0"),
+    "xxz_chain_L24_sz0": dict(n=24, kind="xxz", desc="XXZ chain L=24, Sz=0 (small, for quick checks)"),
+    "xxz_chain_L16_sz0": dict(n=16, kind="xxz", desc="Heisenberg chain L=16, Sz=0 (reference CPU-runnable case)"),
+}
+
+
+def nnz_eff(n_sites: int, n_bonds: int) -> int:
+    """D + n_bonds * 2 * C(N-2, N/2-1)."""
+    return math.comb(n_sites, n_sites // 2) + n_bonds * 2 * math.comb(n_sites - 2, n_sites // 2 - 1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_model(ed, w):
+    n = w["n"]
+    if w["kind"] == "xxz":
+        hs, h = ed.models.xxz_chain(n, 1.0)
+        n_bonds = n
+    else:
+        hs, h = ed.models.j1j2_chain(n, 0.5)
+        n_bonds = 2 * n
+    return hs, h, n_bonds
+
+
+def cpu_baseline(w, target_seconds=12.0, threads=None):
+    """Reference-algorithm restatement (oracle C twin) on a bounded contiguous row sample, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import ed_oracle_c as OC
+    sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
+    import edcuda as ed   # only for the model's term list (host code); no engine compute on this path
+    if threads:
+        OC.set_num_threads(threads)
+    n = w["n"]
+    _, h, n_bonds = build_model(ed, w)
+    terms = h.arrays()
+    basis = OC.basis_fixed_popcount(n, n // 2)
+    dim = len(basis)
+    rng = np.random.default_rng(20260717 + 5)
+    x = rng.standard_normal(dim)
+    # calibrate on a small slice in the middle of the basis, then size the sample for ~target_seconds
+    mid = dim // 2
+    n0 = min(dim, 20000 * OC.num_threads())
+    lo0 = max(0, mid - n0 // 2)
+    out = np.zeros(n0)
+    t0 = time.perf_counter()
+    OC.apply(basis, terms, x, out, lo0, lo0 + n0)
+    dt0 = time.perf_counter() - t0
+    rows = int(min(dim, max(n0, n0 * target_seconds / max(dt0, 1e-6))))
+    lo = max(0, mid - rows // 2)
+    out = np.zeros(rows)
+    t0 = time.perf_counter()
+    OC.apply(basis, terms, x, out, lo, lo + rows)
+    dt = time.perf_counter() - t0
+    matvec_s = dt * dim / rows
+    return {"value": 1.0 / matvec_s, "unit": "matvec/s", "cores": OC.num_threads(), "kind": "port",
+            "sample": f"rows [{lo},{lo + rows}) of {dim} ({rows / dim:.4%}) timed {dt:.2f}s on {OC.num_threads()} OpenMP threads, "
+                      f"extrapolated to the full matvec; reference-algorithm restatement (oracle/ed_oracle_c.c), not Julia",
+            "seconds_per_matvec_extrapolated": matvec_s, "gnnz_per_s": nnz_eff(n, n_bonds) / matvec_s / 1e9}
+
+
+def run_reference(args, w, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(w, target_seconds=per_step)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = sum(vals) / len(vals)
+    n = w["n"]
+    n_bonds = n if w["kind"] == "xxz" else 2 * n
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "H*v matvecs/sec", "value": v, "unit": "matvec/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gnnz_per_s": nnz_eff(n, n_bonds) * v / 1e9,
+            "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": math.comb(n, n // 2)},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="edcuda")
+    ap.add_argument("--workload", default="xxz_chain_L32_sz0")
+    ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    name = args.workload
+    w = WORKLOADS[name]
+    if args.impl == "reference":
+        run_reference(args, w, name)
+        return
+
+    import numpy as np
+    import torch
+    import edcuda as ed
+    from edcuda.lanczos import ShardedMatvec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if ed.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; libedcuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    from edcuda._lib import lib, check
+    check(lib.ed_set_device(local_rank))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    n = w["n"]
+    hs, h, n_bonds = build_model(ed, w)
+    hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
+    dim = hsr.dimension
+    opr = ed.represent(hsr, h).set_kernel(args.kernel)
+    mv = ShardedMatvec(opr, rank, world, np.float64)
+    n_local = mv.hi - mv.lo
+    # synthetic input: Philox normal vector keyed by the global row index (shard-count independent)
+    x_local = torch.empty(n_local, dtype=torch.float64, device=dev)
+    y_local = torch.zeros(n_local, dtype=torch.float64, device=dev)
+    import ctypes as C
+    check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+    check(lib.ed_vector_randn_async(x_local.data_ptr(), n_local, ed.ED_F64, 20260717 + 5, mv.lo))
+    lib.ed_set_stream(None, 0)
+    x_local.mul_(1.0 / math.sqrt(dim))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        mv.matvec(y_local, x_local)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ed.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for i in range(args.steps):
+        if world > 1:
+            xf = mv.gather(x_local)
+        else:
+            xf = x_local          # one GPU owns every row: the local vector is the full vector
+        kev[i][0].record()
+        mv.apply_local(y_local, xf)
+        kev[i][1].record()
+    ev1.record()
+    barrier()
+    launches = ed.kernel_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev0.elapsed_time(ev1)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = 1e3 / ms_per_step
+    checksum = float(torch.dot(x_local, y_local))   # <x, Hx> partial: a sanity value, not timed
+    if world > 1:
+        cs = torch.tensor([checksum], dtype=torch.float64, device=dev)
+        dist.all_reduce(cs)
+        checksum = float(cs[0])
+
+    # ---- e2e: the public call with HOST (pinned) buffers, H2D/D2H inside the timed region --------------
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            xh = torch.empty(dim, dtype=torch.float64).pin_memory()
+            yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
+            xh.copy_(x_local)
+            xn, yn = xh.numpy(), yh.numpy()
+            e_steps = max(2, min(args.steps, 5))
+            ed.mul_b(yn, opr, xn)   # warm-up (allocations)
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                ed.mul_b(yn, opr, xn)
+            dt = (time.perf_counter() - t0) / e_steps
+            assert abs(float(np.dot(xn, yn)) - checksum) <= 1e-9 * max(1.0, abs(checksum))
+            e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(n_local * 8),
+                   "ms_per_step": dt * 1e3, "api": "edcuda.mul_b(out, opr, x) = mul!(out, opr, x) with pinned host vectors -> ed_apply"}
+        else:
+            # every rank holds its rows of x and y in pinned host memory; a step = H2D of the local x rows,
+            # NCCL all-gather, local apply, D2H of the local y rows
+            xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
+            yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
+            xh.copy_(x_local)
+            xd = torch.empty_like(x_local)
+            e_steps = max(2, min(args.steps, 5))
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                xd.copy_(xh, non_blocking=True)
+                mv.matvec(y_local, xd)
+                yh.copy_(y_local, non_blocking=True)
+                torch.cuda.synchronize()
+            barrier()
+            dt = (time.perf_counter() - t0) / e_steps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+            e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(dim * 8),
+                   "ms_per_step": dt * 1e3, "api": "ShardedMatvec.matvec with per-rank pinned host shards (H2D + all-gather + ed_apply_async + D2H)"}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = 24.0 * n_local     # 8 B basis word + 8 B x + 8 B y per owned row
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "H*v matvecs/sec", "value": value, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "gnnz_per_s": nnz_eff(n, n_bonds) * value / 1e9,
+            "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": dim, "n_terms": len(h.terms),
+                       "rows_per_gpu": n_local, "sharding": "rows" if world > 1 else "none",
+                       "exchange": "nccl all_gather of x per matvec" if world > 1 else "none",
+                       "l2": "inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (dim * 8 / 1e9),
+                       "kernel": "generic term-walk" if args.kernel == 1 else "auto",
+                       "checksum_x_dot_Hx": checksum},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8TBs": achieved / 8000.0},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

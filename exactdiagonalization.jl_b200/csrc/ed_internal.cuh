@@ -263,7 +263,7 @@ struct ed_oprep {
   int kernel_choice = 0;
   TermsDev terms_left, terms_right;
   bool terms_ready = false;
-  std::shared_ptr<FastU1Plan> u1plan;
+  std::shared_ptr<FastU1Plan> u1plan, u1plan_c;  // f64 / c128 vectors
   // sparse() result kept between ed_sparse_count and ed_sparse_fetch
   DevBuf<int64_t> sp_colptr, sp_rowval;
   DevBuf<double> sp_nzval;

@@ -686,3 +686,105 @@ def test_lanczos_vs_oracle_and_known_answers(gpu_ed, golden):
     hs12, mg = ed.models.j1j2_chain(12, 0.5)
     res4 = lanczos(ed.represent(ed.represent(ed.HilbertSpaceSector(hs12, 0)), mg), 200, seed=3)
     assert abs(res4.ritz[0] + 18.0) < 1e-10
+
+
+# ------------------------------------------------------------------ K2 fast path (apply_u1.cu)
+def _c_oracle_apply(n, n_dn, op, x, side=0):
+    import ed_oracle_c as OC
+    basis = OC.basis_fixed_popcount(n, n_dn)
+    out = np.zeros_like(x)
+    OC.apply(basis, op.arrays(), x, out, side=side)
+    return basis, out
+
+
+@pytest.mark.parametrize("n,n_dn,model", [(20, 10, "xxz"), (20, 7, "j1j2_field"), (16, 8, "square"), (16, 5, "triangular"),
+                                          (24, 12, "xxz"), (13, 6, "open_chain_disorderfree")])
+def test_fast_path_vs_c_oracle(gpu_ed, n, n_dn, model):
+    """The tiled U(1) kernel against the oracle's C twin (reference algorithm) at sizes the Python oracle cannot
+    reach, for every bond geometry the lowering distinguishes (several distance classes, wrap bonds, fields)."""
+    ed = gpu_ed
+    L = ed.lattices
+    hs, pauli = ed.spin_half_system(n)
+    if model == "xxz":
+        h = ed.models.xxz_bonds(hs, L.chain_bonds(n), 1.0, 0.37)
+    elif model == "j1j2_field":
+        h = ed.simplify(ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 1)) + ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 2), 0.5)
+                        + sum(0.3 * pauli(i, "z") for i in range(0, n, 2)) + 1.25 * ed.Operator([(0, 0, 0, 1.0)]))
+    elif model == "square":
+        h = ed.models.heisenberg_bonds(hs, L.square_bonds(4, 4))
+    elif model == "triangular":
+        h = ed.models.heisenberg_bonds(hs, L.triangular_bonds(4, 4), 0.25)
+    else:
+        h = ed.models.xxz_bonds(hs, L.chain_bonds(n, 1, periodic=False), 0.8, -1.1)
+    hsr = ed.represent(ed.HilbertSpaceSector(hs, n - 2 * n_dn))
+    assert hsr.kind == ed.ED_BASIS_COMBINADIC
+    d = hsr.dimension
+    rng = np.random.default_rng(n + n_dn)
+    x = rng.standard_normal(d)
+    basis, exp = _c_oracle_apply(n, n_dn, h, x)
+    assert np.array_equal(hsr.download(0, d), basis)
+    fast, gen = ed.represent(hsr, h), ed.represent(hsr, h).set_kernel(1)
+    y_fast, y_gen = np.zeros(d), np.zeros(d)
+    ed.mul_b(y_fast, fast, x)
+    ed.mul_b(y_gen, gen, x)
+    assert rel_err(y_gen, exp) < TOL
+    assert rel_err(y_fast, exp) < TOL
+    # apply! accumulates, x*H == H*x for the symmetric real operator, complex vectors
+    ed.apply_b(y_fast, x, fast)
+    assert rel_err(y_fast, 2 * exp) < TOL
+    xc = x + 1j * rng.standard_normal(d)
+    _, expc = _c_oracle_apply(n, n_dn, h, xc)
+    yc = np.zeros(d, dtype=complex)
+    ed.mul_b(yc, fast, xc)
+    assert rel_err(yc, expc) < TOL
+    # row shards through the fast path
+    cuts = [0, d // 7, d // 2 + 3, d]
+    parts = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        out = np.zeros(hi - lo)
+        ed.mul_b(out, ed.represent(hsr, h).set_rows(lo, hi), x)
+        parts.append(out)
+    assert rel_err(np.concatenate(parts), exp) < TOL
+
+
+def test_fast_path_falls_back_for_unsupported_operators(gpu_ed):
+    ed = gpu_ed
+    n = 10
+    hs, pauli = ed.spin_half_system(n)
+    hs_o, pauli_o = O.spin_half_system(n)
+    # three-site term and asymmetric hopping: not expressible as symmetric bond exchange -> generic kernel, same answer
+    op = ed.simplify(pauli(0, "z") * pauli(1, "+") * pauli(2, "-") + 0.5 * pauli(3, "+") * pauli(4, "-")
+                     + ed.models.heisenberg_bonds(hs, ed.lattices.chain_bonds(n)))
+    op_o = O.simplify(pauli_o(0, "z") * pauli_o(1, "+") * pauli_o(2, "-") + 0.5 * (pauli_o(3, "+") * pauli_o(4, "-"))
+                      + oracle_spin_chain(n)[1])
+    assert op.terms == terms_of(op_o)
+    hsr, hsr_o = ed.represent(ed.HilbertSpaceSector(hs, 0)), O.represent(O.HilbertSpaceSector(hs_o, 0))
+    _check_apply(ed, hsr, hsr_o, op, op_o, False)
+
+
+def test_full_size_properties_l28(gpu_ed):
+    """Config 3 (J1-J2 chain L=28, Sz=0, D = 40,116,600) at full size through size-independent properties:
+    fast kernel == generic kernel, symmetry <x,Hy> = <Hx,y>, linearity, Majumdar-Ghosh ground energy -1.5 L."""
+    ed = gpu_ed
+    import torch
+    from edcuda.lanczos import lanczos
+    hs, h = ed.models.j1j2_chain(28, 0.5)
+    hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
+    d = hsr.dimension
+    assert d == 40116600
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(d, dtype=torch.float64, device="cuda", generator=g)
+    z = torch.randn(d, dtype=torch.float64, device="cuda", generator=g)
+    fast, gen = ed.represent(hsr, h), ed.represent(hsr, h).set_kernel(1)
+    hx_f, hx_g, hz = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    ed.mul_b(hx_f, fast, x)
+    ed.mul_b(hx_g, gen, x)
+    ed.mul_b(hz, fast, z)
+    torch.cuda.synchronize()
+    assert float((hx_f - hx_g).abs().max() / hx_g.abs().max()) < TOL
+    assert abs(float(torch.dot(z, hx_f) - torch.dot(hz, x))) < 1e-10 * float(hx_f.norm() * z.norm())
+    comb = torch.empty_like(x)
+    ed.mul_b(comb, fast, 2.0 * x - 0.5 * z)
+    assert float((comb - (2.0 * hx_f - 0.5 * hz)).abs().max() / hx_f.abs().max()) < TOL
+    res = lanczos(fast, 160, seed=5)
+    assert abs(res.ritz[0] + 42.0) < 1e-9

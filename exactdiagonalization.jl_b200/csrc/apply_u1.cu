@@ -29,26 +29,36 @@
 
 void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
 
-#define U1_MAX_CLASSES 12
+#define U1_MAX_CLASSES 8
 #define U1_MAX_HH 192
 #define U1_MAX_MX 64
+#define U1_MAX_MQ 64
 
+// Everything that depends only on the LOW k bits of a row is tabulated once per plan (tables live in L2):
+//   dcode / dval   diagonal of the low-bit terms (u8 code -> value)
+//   ell            for every exchange class, the local column indices of the firing low-bit bonds in ELL form
+//                  (slot-major, padded with a dummy index that points at a zero in shared memory)
+//   mx_tab         local column index inside the neighbouring tile for every bond straddling bit k
 struct U1Params {
   int n_bits, n_set, k;
-  int t1_stride;                // 2^(max(k-8,0))
   uint32_t tile_cap;            // largest tile (rows)
   const uint32_t* tile_H;       // [n_tiles] non-empty tiles in ascending H
   const uint64_t* tile_base;    // [2^(n_bits-k)] rank of the first row of tile H
+  const double* tile_diag;      // [2^(n_bits-k)] constant + diagonal terms that depend on H only
   const uint16_t* lowword;      // [2^k] k-bit words sorted by (popcount, value)
-  const uint32_t* lowofs;       // [k+2]
-  const uint16_t* T0;           // [256]
-  const uint16_t* T1;           // [9 * t1_stride]
-  double dconst;
-  int n_lin;  uint64_t lin_mask[U1_MAX_CLASSES];  double lin_coef[U1_MAX_CLASSES];
-  int n_quad; int quad_d[U1_MAX_CLASSES]; uint64_t quad_mask[U1_MAX_CLASSES]; double quad_coef[U1_MAX_CLASSES];
-  int n_ll;   int ll_d[U1_MAX_CLASSES];   uint32_t ll_mask[U1_MAX_CLASSES];   double ll_amp[U1_MAX_CLASSES];
-  int n_hh;   const uint8_t* hh_p; const uint8_t* hh_q; const double* hh_amp;   // positions inside H
-  int n_mx;   const uint8_t* mx_p; const uint8_t* mx_q; const double* mx_amp;   // p: low bit, q: bit inside H
+  const uint32_t* lowofs;       // [k+2] first row of popcount p in the tables
+  const uint32_t* grpofs;       // [k+2] first 32-row group of popcount p
+  int diag_mode;                // 0: no low-bit diagonal, 1: u8 code + dval, 2: f64 table
+  const uint8_t* dcode;         // [2^k]
+  const double* dval;           // [256]
+  const double* dlow;           // [2^k]
+  int n_mq; const uint8_t* mq_p; const uint8_t* mq_q; const double* mq_coef;   // n_p n_q terms straddling bit k
+  int n_ll; double ll_amp[U1_MAX_CLASSES];
+  const uint16_t* ell[U1_MAX_CLASSES];     // class tables
+  const uint8_t* ell_cnt[U1_MAX_CLASSES];  // slots used per 32-row group
+  const uint32_t* ell_ofs;                 // [n_ll * (k+1)] start of popcount p inside ell[c]
+  int n_hh;   const uint8_t* hh_p; const uint8_t* hh_q; const double* hh_amp;   // exchange bonds inside H
+  int n_mx;   const uint8_t* mx_q; const double* mx_amp; const uint16_t* mx_tab; // straddling exchange bonds
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
@@ -60,11 +70,14 @@ struct FastU1Plan {
   int n_tiles = 0;
   size_t smem_bytes = 0;
   int vec_bytes = 8;
-  DevBuf<uint32_t> tile_H, lowofs;
+  bool idx32 = true;
+  DevBuf<uint32_t> tile_H, lowofs, grpofs, ell_ofs;
   DevBuf<uint64_t> tile_base;
-  DevBuf<uint16_t> lowword, T0, T1;
-  DevBuf<uint8_t> hh_p, hh_q, mx_p, mx_q;
-  DevBuf<double> hh_amp, mx_amp;
+  DevBuf<uint16_t> lowword, mx_tab;
+  DevBuf<uint8_t> dcode, hh_p, hh_q, mx_q, mq_p, mq_q;
+  DevBuf<double> tile_diag, dval, dlow, hh_amp, mx_amp, mq_coef;
+  std::vector<DevBuf<uint16_t>> ell;
+  std::vector<DevBuf<uint8_t>> ell_cnt;
   DevBuf<double> partials;
   std::vector<uint64_t> h_base, h_size;  // per non-empty tile, ascending
 };
@@ -81,22 +94,21 @@ __device__ __forceinline__ void vec_fma(c128& acc, double a, c128 v) { acc.re = 
 __device__ __forceinline__ double vec_add(double a, double b) { return a + b; }
 __device__ __forceinline__ c128 vec_add(c128 a, c128 b) { return cadd(a, b); }
 
-template <typename WordT> __device__ __forceinline__ int popc_w(WordT v);
-template <> __device__ __forceinline__ int popc_w<uint32_t>(uint32_t v) { return __popc(v); }
-template <> __device__ __forceinline__ int popc_w<uint64_t>(uint64_t v) { return __popcll(v); }
-
-template <typename VecT, typename WordT, int THREADS>
+// One CTA = one tile; every thread owns R rows (i = tid + r*THREADS) whose accumulators stay in registers, so
+// every bond / slot loop has R independent loads in flight per thread (the kernel is latency-bound otherwise).
+template <typename VecT, typename IdxT, int THREADS, int R>
 __global__ void __launch_bounds__(THREADS, 2)
 k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  VecT* xs = reinterpret_cast<VecT*>(smem_raw);
-  uint64_t* hh_base = reinterpret_cast<uint64_t*>(xs + P.tile_cap);
-  double* hh_amp = reinterpret_cast<double*>(hh_base + U1_MAX_HH);
-  uint64_t* mx_base = reinterpret_cast<uint64_t*>(hh_amp + U1_MAX_HH);
-  double* mx_amp = reinterpret_cast<double*>(mx_base + U1_MAX_MX);
-  uint32_t* mx_info = reinterpret_cast<uint32_t*>(mx_amp + U1_MAX_MX);   // low bit position | (H bit value << 8)
-  uint16_t* sT0 = reinterpret_cast<uint16_t*>(mx_info + U1_MAX_MX);
-  uint16_t* sT1 = sT0 + 256;
+  VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
+  double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 1);
+  double* mx_amp = hh_amp + U1_MAX_HH;
+  double* mq_coef = mx_amp + U1_MAX_MX;
+  double* s_dval = mq_coef + U1_MAX_MQ;                                // 256
+  IdxT* hh_base = reinterpret_cast<IdxT*>(s_dval + 256);
+  IdxT* mx_base = hh_base + U1_MAX_HH;
+  uint32_t* mx_toff = reinterpret_cast<uint32_t*>(mx_base + U1_MAX_MX);
+  uint32_t* mq_bit = mx_toff + U1_MAX_MX;
   __shared__ int s_counts[2];
 
   const int tid = threadIdx.x;
@@ -104,10 +116,11 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
   const int p_low = P.n_set - __popc(H);
   const uint32_t lofs = P.lowofs[p_low];
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
-  const uint64_t base = P.tile_base[H];
+  const uint32_t gofs = P.grpofs[p_low];
+  const IdxT base = (IdxT)P.tile_base[H];
   const int k = P.k;
 
-  // ---- prologue: per-tile bond lists (deterministic ballot compaction), rank LUTs, x tile ---------------
+  // ---- prologue: per-tile bond lists (deterministic ballot compaction), x tile --------------------------
   if (tid < 32) {
     int n = 0;
     for (int b0 = 0; b0 < P.n_hh; b0 += 32) {
@@ -122,7 +135,7 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (fire) {
         const int slot = n + __popc(m & ((1u << tid) - 1u));
-        hh_base[slot] = P.tile_base[H2];
+        hh_base[slot] = (IdxT)P.tile_base[H2];
         hh_amp[slot] = P.hh_amp[b];
       }
       n += __popc(m);
@@ -133,69 +146,130 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
     for (int b = lane; b < P.n_mx; b += 32) {
       const int q = P.mx_q[b];
       const uint32_t hbit = (H >> q) & 1u;
-      mx_base[b] = P.tile_base[H ^ (1u << q)];
+      mx_base[b] = (IdxT)P.tile_base[H ^ (1u << q)];
       mx_amp[b] = P.mx_amp[b];
-      mx_info[b] = (uint32_t)P.mx_p[b] | (hbit << 8);
+      mx_toff[b] = ((uint32_t)(2 * b + hbit) << k) + lofs;
     }
+  } else if (tid < 96) {
+    const int lane = tid - 64;
+    int n = 0;
+    for (int b0 = 0; b0 < P.n_mq; b0 += 32) {
+      const int b = b0 + lane;
+      const bool on = b < P.n_mq && ((H >> P.mq_q[b]) & 1u);
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int slot = n + __popc(m & ((1u << lane) - 1u));
+        mq_bit[slot] = P.mq_p[b];
+        mq_coef[slot] = P.mq_coef[b];
+      }
+      n += __popc(m);
+    }
+    if (lane == 0) s_counts[1] = n;
   }
-  for (int i = tid; i < 256; i += THREADS) sT0[i] = P.T0[i];
-  for (int i = tid; i < 9 * P.t1_stride; i += THREADS) sT1[i] = P.T1[i];
-  for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(x + base + i);
+  if (P.diag_mode == 1) for (int i = tid; i < 256; i += THREADS) s_dval[i] = P.dval[i];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint32_t i = tid + r * THREADS;
+    if (i < size) xs[i] = ldg_val(x + (base + i));
+  }
+  if (tid == 0) xs[size] = vzero((VecT*)nullptr);
   __syncthreads();
   const int n_hh = s_counts[0];
+  const int n_mq = s_counts[1];
   const int n_mx = P.n_mx;
-  const int t1s = P.t1_stride;
+  const double d_tile = P.tile_diag[H];
 
+  // rows of this thread: i_r = tid + r*THREADS; `live` = inside the tile and inside the owned row range
+  VecT acc[R];
+  bool live[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const uint32_t i = tid + r * THREADS;
+    const int64_t row = (int64_t)base + i;
+    live[r] = i < size && row >= P.row_lo && row < P.row_hi;
+    acc[r] = vzero((VecT*)nullptr);
+  }
+  // diagonal
+  if (P.diag_mode == 1) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (live[r]) { const uint32_t i = tid + r * THREADS; acc[r] = vec_scale<VecT>(d_tile + s_dval[__ldg(P.dcode + lofs + i)], xs[i]); }
+  } else if (P.diag_mode == 2) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (live[r]) { const uint32_t i = tid + r * THREADS; acc[r] = vec_scale<VecT>(d_tile + __ldg(P.dlow + lofs + i), xs[i]); }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (live[r]) acc[r] = vec_scale<VecT>(d_tile, xs[tid + r * THREADS]);
+  }
+  if (n_mq) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (live[r]) {
+        const uint32_t i = tid + r * THREADS;
+        const uint32_t low = __ldg(P.lowword + lofs + i);
+        double d = 0.0;
+        for (int e = 0; e < n_mq; ++e) d += ((low >> mq_bit[e]) & 1u) ? mq_coef[e] : 0.0;
+        vec_fma(acc[r], d, xs[i]);
+      }
+  }
+  // bonds inside the high bits: same local index in another tile -> R coalesced streams in flight
+#pragma unroll 1
+  for (int e = 0; e < n_hh; ++e) {
+    const double a = hh_amp[e];
+    const VecT* xe = x + hh_base[e];
+    VecT v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = live[r] ? ldg_val(xe + (tid + r * THREADS)) : vzero((VecT*)nullptr);
+#pragma unroll
+    for (int r = 0; r < R; ++r) vec_fma(acc[r], a, v[r]);
+  }
+  // exchange bonds inside the low k bits: ELL table of local columns, shared-memory gathers
+#pragma unroll 1
+  for (int c = 0; c < P.n_ll; ++c) {
+    const uint8_t* cnt = P.ell_cnt[c] + gofs;
+    int nmax = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (live[r]) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // uniform across the warp
+    const uint16_t* e = P.ell[c] + P.ell_ofs[c * (k + 1) + p_low] + tid;
+    const double a = P.ll_amp[c];
+#pragma unroll 1
+    for (int sl = 0; sl < nmax; ++sl) {
+      uint32_t j[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) j[r] = live[r] ? (uint32_t)__ldg(e + r * THREADS) : size;   // padding -> xs[size] == 0
+#pragma unroll
+      for (int r = 0; r < R; ++r) vec_fma(acc[r], a, xs[j[r]]);
+      e += size;
+    }
+  }
+  // bonds straddling bit k: tabulated local column inside the neighbouring tile
+#pragma unroll 1
+  for (int e = 0; e < n_mx; ++e) {
+    const uint16_t* tab = P.mx_tab + mx_toff[e] + tid;
+    const VecT* xe = x + mx_base[e];
+    const double a = mx_amp[e];
+    uint32_t j[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) j[r] = live[r] ? (uint32_t)__ldg(tab + r * THREADS) : 0xFFFFu;
+    VecT v[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[r] = j[r] != 0xFFFFu ? ldg_val(xe + j[r]) : vzero((VecT*)nullptr);
+#pragma unroll
+    for (int r = 0; r < R; ++r) vec_fma(acc[r], a, v[r]);
+  }
   double dre = 0.0, dim_ = 0.0;
-  for (uint32_t i = tid; i < size; i += THREADS) {
-    const int64_t row = (int64_t)(base + i);
-    if (row < P.row_lo || row >= P.row_hi) continue;
-    const uint32_t low = __ldg(P.lowword + lofs + i);
-    const WordT s = ((WordT)H << k) | (WordT)low;
-    // diagonal: const + sum coef * popcount(...)
-    double d = P.dconst;
-#pragma unroll 1
-    for (int c = 0; c < P.n_lin; ++c) d = fma(P.lin_coef[c], (double)popc_w<WordT>(s & (WordT)P.lin_mask[c]), d);
-#pragma unroll 1
-    for (int c = 0; c < P.n_quad; ++c)
-      d = fma(P.quad_coef[c], (double)popc_w<WordT>(s & (s >> P.quad_d[c]) & (WordT)P.quad_mask[c]), d);
-    const VecT xi = xs[i];
-    VecT acc = vec_scale<VecT>(d, xi);
-    // exchange bonds inside the low k bits: shared-memory gathers
-#pragma unroll 1
-    for (int c = 0; c < P.n_ll; ++c) {
-      const int dd = P.ll_d[c];
-      uint32_t t = (low ^ (low >> dd)) & P.ll_mask[c];
-      const double a = P.ll_amp[c];
-      const uint32_t pair = 1u | (1u << dd);
-      while (t) {
-        const int q = __ffs(t) - 1;
-        t &= t - 1;
-        const uint32_t low2 = low ^ (pair << q);
-        const uint32_t b0 = low2 & 255u;
-        const uint32_t j = (uint32_t)sT0[b0] + (uint32_t)sT1[__popc(b0) * t1s + (low2 >> 8)];
-        vec_fma(acc, a, xs[j]);
-      }
-    }
-    // bonds straddling bit k: gather from the neighbouring tile
-#pragma unroll 1
-    for (int e = 0; e < n_mx; ++e) {
-      const uint32_t info = mx_info[e];
-      const int p = info & 255u;
-      if (((low >> p) & 1u) != (info >> 8)) {
-        const uint32_t low2 = low ^ (1u << p);
-        const uint32_t b0 = low2 & 255u;
-        const uint32_t j = (uint32_t)sT0[b0] + (uint32_t)sT1[__popc(b0) * t1s + (low2 >> 8)];
-        vec_fma(acc, mx_amp[e], ldg_val(x + mx_base[e] + j));
-      }
-    }
-    // bonds inside the high bits: same local index in another tile, coalesced
-#pragma unroll 4
-    for (int e = 0; e < n_hh; ++e) vec_fma(acc, hh_amp[e], ldg_val(x + hh_base[e] + i));
-    VecT* dst = y + (row - P.row_lo);
-    if (P.accumulate) acc = vec_add(acc, *dst);
-    st_val(dst, acc);
-    if (dot_partials) dot_acc(dre, dim_, xi, acc);
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (!live[r]) continue;
+    const uint32_t i = tid + r * THREADS;
+    VecT* dst = y + ((int64_t)base + i - P.row_lo);
+    VecT out = acc[r];
+    if (P.accumulate) out = vec_add(out, *dst);
+    st_val(dst, out);
+    if (dot_partials) dot_acc(dre, dim_, xs[i], out);
   }
   if (dot_partials) {
     __shared__ double s_red[2][THREADS / 32];
@@ -300,8 +374,8 @@ int choose_k(int n_bits, int vec_bytes) {
     int v = atoi(e);
     if (v >= 1 && v <= 16) k = std::min(v, n_bits);
   }
-  // x tile must leave room for two CTAs per SM: <= 104 KB
-  while (k > 1 && binom_u64(k, k / 2) * (uint64_t)vec_bytes > 104 * 1024) --k;
+  // x tile must leave room for two CTAs per SM (<= 104 KB) and at most 13 register-resident rows per thread
+  while (k > 1 && (binom_u64(k, k / 2) * (uint64_t)vec_bytes > 104 * 1024 || binom_u64(k, k / 2) > (uint64_t)(vec_bytes == 8 ? 13 : 7) * 512)) --k;
   return k;
 }
 
@@ -313,26 +387,94 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   plan->vec_bytes = vec_bytes;
   if (b->kind != ED_BASIS_COMBINADIC || b->dim <= 0) return plan;
   const int n_bits = b->space.bits, n_set = b->n_set;
-  if (n_bits < 1 || n_bits > 48) return plan;
+  if (n_bits < 1 || n_bits > 42) return plan;
   Lowered L = lower_operator(o->op, n_bits, n_set);
   if (!L.ok) return plan;
-  if ((int)L.lin.size() > U1_MAX_CLASSES || (int)L.quad.size() > U1_MAX_CLASSES) return plan;
   const int k = choose_k(n_bits, vec_bytes);
   const int hb = n_bits - k;
   if (hb > 26) return plan;  // tile tables of 2^hb entries
   U1Params& P = plan->P;
   memset(&P, 0, sizeof(P));
   P.n_bits = n_bits; P.n_set = n_set; P.k = k;
-  P.t1_stride = 1 << std::max(k - 8, 0);
-  P.dconst = L.dconst;
-  P.n_lin = (int)L.lin.size();
-  for (int c = 0; c < P.n_lin; ++c) { P.lin_coef[c] = L.lin[c].first; P.lin_mask[c] = L.lin[c].second; }
-  P.n_quad = (int)L.quad.size();
-  for (int c = 0; c < P.n_quad; ++c) { P.quad_d[c] = L.quad[c].d; P.quad_coef[c] = L.quad[c].v; P.quad_mask[c] = L.quad[c].mask; }
-  // split the exchange bonds at bit k
+  plan->idx32 = b->dim < (1ll << 32);
+  const uint32_t nlow = 1u << k;
+  const uint32_t nH = 1u << hb;
+  const uint64_t lowmask = (1ull << k) - 1ull;
+
+  // ---- low-word enumeration ------------------------------------------------------------------------------
+  std::vector<uint32_t> lowofs(k + 2, 0), grpofs(k + 2, 0);
+  for (int p = 0; p <= k; ++p) {
+    lowofs[p + 1] = lowofs[p] + (uint32_t)binom_u64(k, p);
+    grpofs[p + 1] = grpofs[p] + (uint32_t)((binom_u64(k, p) + 31) / 32);
+  }
+  std::vector<uint16_t> lowword(nlow);
+  std::vector<uint32_t> lowrank(nlow);   // index inside its popcount class
+  {
+    std::vector<uint32_t> at(k + 1, 0);
+    for (uint32_t w = 0; w < nlow; ++w) {
+      const int p = __builtin_popcount(w);
+      lowrank[w] = at[p];
+      lowword[lowofs[p] + at[p]++] = (uint16_t)w;
+    }
+  }
+
+  // ---- diagonal: split into H-only (per tile), low-only (tabulated) and straddling n_p n_q terms ----------
+  std::vector<double> tile_diag(nH, 0.0), dlow(nlow, 0.0);
+  std::vector<uint8_t> mq_p, mq_q;
+  std::vector<double> mq_coef;
+  for (uint32_t H = 0; H < nH; ++H) {
+    double d = L.dconst;
+    const uint64_t s = (uint64_t)H << k;
+    for (auto& l : L.lin) d += l.first * __builtin_popcountll(s & l.second & ~lowmask);
+    for (auto& q : L.quad) {
+      const uint64_t hm = q.mask & ~lowmask;   // lower site already inside H
+      d += q.v * __builtin_popcountll(s & (s >> q.d) & hm);
+    }
+    tile_diag[H] = d;
+  }
+  bool any_low_diag = false;
+  for (uint32_t w = 0; w < nlow; ++w) {
+    double d = 0;
+    for (auto& l : L.lin) d += l.first * __builtin_popcountll((uint64_t)w & l.second & lowmask);
+    for (auto& q : L.quad) {
+      uint64_t m = 0;   // bonds with both sites inside the low bits
+      for (int p = 0; p + q.d < k; ++p) if (q.mask >> p & 1) m |= 1ull << p;
+      d += q.v * __builtin_popcountll((uint64_t)w & ((uint64_t)w >> q.d) & m);
+    }
+    dlow[lowofs[__builtin_popcount(w)] + lowrank[w]] = d;
+    if (d != 0.0) any_low_diag = true;
+  }
+  for (auto& q : L.quad)
+    for (int p = 0; p < k; ++p)
+      if ((q.mask >> p & 1) && p + q.d >= k) { mq_p.push_back((uint8_t)p); mq_q.push_back((uint8_t)(p + q.d - k)); mq_coef.push_back(q.v); }
+  if ((int)mq_p.size() > U1_MAX_MQ) return plan;
+  P.n_mq = (int)mq_p.size();
+  std::vector<double> dval;
+  std::vector<uint8_t> dcode(nlow, 0);
+  if (!any_low_diag) P.diag_mode = 0;
+  else {
+    std::map<double, int> codes;
+    bool fits = true;
+    for (uint32_t i = 0; i < nlow && fits; ++i) {
+      auto it = codes.find(dlow[i]);
+      if (it == codes.end()) {
+        if (codes.size() >= 256) { fits = false; break; }
+        it = codes.emplace(dlow[i], (int)codes.size()).first;
+      }
+      dcode[i] = (uint8_t)it->second;
+    }
+    if (fits) {
+      P.diag_mode = 1;
+      dval.assign(256, 0.0);
+      for (auto& kv : codes) dval[kv.second] = kv.first;
+    } else P.diag_mode = 2;
+  }
+
+  // ---- exchange bonds: split at bit k --------------------------------------------------------------------
   std::vector<uint8_t> hh_p, hh_q, mx_p, mx_q;
   std::vector<double> hh_amp, mx_amp;
-  const uint64_t lowmask = (1ull << k) - 1ull;
+  struct LL { int d; uint32_t mask; double amp; };
+  std::vector<LL> lls;
   for (auto& c : L.exch) {
     uint64_t ll = 0;
     for (int p = 0; p < n_bits; ++p) {
@@ -342,69 +484,109 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
       else if (p >= k) { hh_p.push_back((uint8_t)(p - k)); hh_q.push_back((uint8_t)(q - k)); hh_amp.push_back(c.v); }
       else { mx_p.push_back((uint8_t)p); mx_q.push_back((uint8_t)(q - k)); mx_amp.push_back(c.v); }
     }
-    if (ll) {
-      if (P.n_ll >= U1_MAX_CLASSES) return plan;
-      P.ll_d[P.n_ll] = c.d; P.ll_mask[P.n_ll] = (uint32_t)(ll & lowmask); P.ll_amp[P.n_ll] = c.v;
-      ++P.n_ll;
-    }
+    if (ll) lls.push_back({c.d, (uint32_t)(ll & lowmask), c.v});
   }
+  // classes with the same amplitude share one ELL table
+  std::map<double, std::vector<LL>> by_amp;
+  for (auto& l : lls) by_amp[l.amp].push_back(l);
+  if ((int)by_amp.size() > U1_MAX_CLASSES) return plan;
   if ((int)hh_p.size() > U1_MAX_HH || (int)mx_p.size() > U1_MAX_MX) return plan;
   P.n_hh = (int)hh_p.size();
   P.n_mx = (int)mx_p.size();
-  // low-word tables
-  std::vector<uint32_t> lowofs(k + 2, 0);
-  for (int p = 0; p <= k; ++p) lowofs[p + 1] = lowofs[p] + (uint32_t)binom_u64(k, p);
-  std::vector<uint16_t> lowword((size_t)1 << k);
+  P.n_ll = (int)by_amp.size();
+  std::vector<uint32_t> ell_ofs((size_t)std::max(P.n_ll, 1) * (k + 1), 0);
+  plan->ell.resize(P.n_ll);
+  plan->ell_cnt.resize(P.n_ll);
   {
-    std::vector<uint32_t> at(lowofs.begin(), lowofs.end());
-    for (uint32_t w = 0; w < (1u << k); ++w) lowword[at[__builtin_popcount(w)]++] = (uint16_t)w;
-  }
-  std::vector<uint16_t> T0(256, 0), T1((size_t)9 * P.t1_stride, 0);
-  for (int byte = 0; byte < 256; ++byte) {
-    uint64_t acc = 0; int i = 0;
-    for (int q = 0; q < 8; ++q) if (byte >> q & 1) { acc += binom_u64(q, i + 1); ++i; }
-    T0[byte] = (uint16_t)acc;
-  }
-  for (int pc0 = 0; pc0 <= 8; ++pc0)
-    for (int hi = 0; hi < P.t1_stride; ++hi) {
-      uint64_t acc = 0; int i = 0;
-      for (int q = 0; q < 8; ++q) if (hi >> q & 1) { acc += binom_u64(8 + q, pc0 + i + 1); ++i; }
-      T1[(size_t)pc0 * P.t1_stride + hi] = (uint16_t)acc;
+    int c = 0;
+    std::vector<uint16_t> nb;
+    for (auto& kv : by_amp) {
+      P.ll_amp[c] = kv.first;
+      std::vector<uint16_t> table;
+      std::vector<uint8_t> cnt(grpofs[k + 1], 0);
+      for (int p = 0; p <= k; ++p) {
+        const uint32_t size = lowofs[p + 1] - lowofs[p];
+        // neighbour lists of every row of this popcount
+        std::vector<std::vector<uint16_t>> lists(size);
+        uint32_t maxslot = 0;
+        for (uint32_t i = 0; i < size; ++i) {
+          const uint32_t w = lowword[lowofs[p] + i];
+          for (auto& l : kv.second) {
+            uint32_t t = (w ^ (w >> l.d)) & l.mask;
+            while (t) {
+              const int q = __builtin_ctz(t);
+              t &= t - 1;
+              lists[i].push_back((uint16_t)lowrank[w ^ ((1u | (1u << l.d)) << q)]);
+            }
+          }
+          maxslot = std::max<uint32_t>(maxslot, (uint32_t)lists[i].size());
+          uint8_t& g = cnt[grpofs[p] + i / 32];
+          g = std::max<uint8_t>(g, (uint8_t)lists[i].size());
+        }
+        ell_ofs[(size_t)c * (k + 1) + p] = (uint32_t)table.size();
+        const size_t start = table.size();
+        table.resize(start + (size_t)maxslot * size, (uint16_t)size);   // padding -> xs[size] == 0
+        for (uint32_t i = 0; i < size; ++i)
+          for (size_t sl = 0; sl < lists[i].size(); ++sl) table[start + sl * size + i] = lists[i][sl];
+      }
+      if (table.empty()) table.push_back(0);
+      plan->ell[c].upload(table);
+      plan->ell_cnt[c].upload(cnt);
+      ++c;
     }
-  // tiles
-  const uint32_t nH = 1u << hb;
+  }
+  // straddling bonds: local column in the neighbouring tile, per (bond, value of the H bit)
+  std::vector<uint16_t> mx_tab((size_t)std::max(P.n_mx, 1) * 2 * nlow, 0xFFFF);
+  for (int e = 0; e < P.n_mx; ++e)
+    for (uint32_t hbit = 0; hbit < 2; ++hbit)
+      for (uint32_t w = 0; w < nlow; ++w) {
+        if (((w >> mx_p[e]) & 1u) == hbit) continue;                 // fires only when the two bits differ
+        const uint32_t w2 = w ^ (1u << mx_p[e]);
+        mx_tab[((size_t)(2 * e + hbit) << k) + lowofs[__builtin_popcount(w)] + lowrank[w]] = (uint16_t)lowrank[w2];
+      }
+
+  // ---- tiles ---------------------------------------------------------------------------------------------
   std::vector<uint64_t> tile_base(nH, 0);
   std::vector<uint32_t> tile_H;
   uint32_t tile_cap = 1;
-  {
+  for (uint32_t H = 0; H < nH; ++H) {
+    const int p_low = n_set - __builtin_popcount(H);
+    if (p_low < 0 || p_low > k) continue;
     // rank of (H << k | lowest word with p_low bits) = sum over set bits of H of C(k + pos, p_low + idx + 1)
-    for (uint32_t H = 0; H < nH; ++H) {
-      const int p_low = n_set - __builtin_popcount(H);
-      if (p_low < 0 || p_low > k) continue;
-      uint64_t acc = 0; int i = 0;
-      for (int q = 0; q < hb; ++q) if (H >> q & 1) { acc += binom_u64(k + q, p_low + i + 1); ++i; }
-      tile_base[H] = acc;
-      tile_H.push_back(H);
-      plan->h_base.push_back(acc);
-      plan->h_size.push_back(binom_u64(k, p_low));
-      tile_cap = std::max<uint32_t>(tile_cap, (uint32_t)binom_u64(k, p_low));
-    }
+    uint64_t acc = 0; int i = 0;
+    for (int q = 0; q < hb; ++q) if (H >> q & 1) { acc += binom_u64(k + q, p_low + i + 1); ++i; }
+    tile_base[H] = acc;
+    tile_H.push_back(H);
+    plan->h_base.push_back(acc);
+    plan->h_size.push_back(binom_u64(k, p_low));
+    tile_cap = std::max<uint32_t>(tile_cap, (uint32_t)binom_u64(k, p_low));
   }
   P.tile_cap = tile_cap;
   plan->n_tiles = (int)tile_H.size();
-  plan->tile_H.upload(tile_H); plan->tile_base.upload(tile_base);
-  plan->lowword.upload(lowword); plan->lowofs.upload(lowofs);
-  plan->T0.upload(T0); plan->T1.upload(T1);
-  if (hh_p.empty()) { hh_p.push_back(0); hh_q.push_back(0); hh_amp.push_back(0); }
-  if (mx_p.empty()) { mx_p.push_back(0); mx_q.push_back(0); mx_amp.push_back(0); }
+
+  auto nonempty8 = [](std::vector<uint8_t>& v) { if (v.empty()) v.push_back(0); };
+  auto nonemptyd = [](std::vector<double>& v) { if (v.empty()) v.push_back(0.0); };
+  nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q);
+  nonemptyd(hh_amp); nonemptyd(mx_amp); nonemptyd(mq_coef); nonemptyd(dval);
+  plan->tile_H.upload(tile_H); plan->tile_base.upload(tile_base); plan->tile_diag.upload(tile_diag);
+  plan->lowword.upload(lowword); plan->lowofs.upload(lowofs); plan->grpofs.upload(grpofs);
+  plan->dcode.upload(dcode); plan->dval.upload(dval); plan->dlow.upload(dlow);
+  plan->mq_p.upload(mq_p); plan->mq_q.upload(mq_q); plan->mq_coef.upload(mq_coef);
+  plan->ell_ofs.upload(ell_ofs);
   plan->hh_p.upload(hh_p); plan->hh_q.upload(hh_q); plan->hh_amp.upload(hh_amp);
-  plan->mx_p.upload(mx_p); plan->mx_q.upload(mx_q); plan->mx_amp.upload(mx_amp);
+  plan->mx_q.upload(mx_q); plan->mx_amp.upload(mx_amp); plan->mx_tab.upload(mx_tab);
   ED_CUDA(cudaStreamSynchronize(ed_stream()));
-  P.tile_H = plan->tile_H.p; P.tile_base = plan->tile_base.p; P.lowword = plan->lowword.p; P.lowofs = plan->lowofs.p;
-  P.T0 = plan->T0.p; P.T1 = plan->T1.p;
+  P.tile_H = plan->tile_H.p; P.tile_base = plan->tile_base.p; P.tile_diag = plan->tile_diag.p;
+  P.lowword = plan->lowword.p; P.lowofs = plan->lowofs.p; P.grpofs = plan->grpofs.p;
+  P.dcode = plan->dcode.p; P.dval = plan->dval.p; P.dlow = plan->dlow.p;
+  P.mq_p = plan->mq_p.p; P.mq_q = plan->mq_q.p; P.mq_coef = plan->mq_coef.p;
+  P.ell_ofs = plan->ell_ofs.p;
+  for (int c = 0; c < P.n_ll; ++c) { P.ell[c] = plan->ell[c].p; P.ell_cnt[c] = plan->ell_cnt[c].p; }
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
-  P.mx_p = plan->mx_p.p; P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p;
-  plan->smem_bytes = (size_t)tile_cap * vec_bytes + U1_MAX_HH * 16 + U1_MAX_MX * (16 + 4) + 256 * 2 + (size_t)9 * P.t1_stride * 2;
+  P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
+  const size_t idx_bytes = plan->idx32 ? 4 : 8;
+  plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
+                     (U1_MAX_HH + U1_MAX_MX) * idx_bytes + (U1_MAX_MX + U1_MAX_MQ) * 4;
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
   plan->supported = true;
   return plan;
@@ -425,16 +607,26 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side) {
   return get_plan(o, dtype)->supported;
 }
 
-template <typename VecT, typename WordT>
-static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
-  constexpr int THREADS = 512;
-  auto kern = k2_apply_u1<VecT, WordT, THREADS>;
+constexpr int U1_THREADS = 512;
+
+template <typename VecT, typename IdxT, int R>
+static void launch_u1_r(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
+  auto kern = k2_apply_u1<VecT, IdxT, U1_THREADS, R>;
   static thread_local size_t configured = 0;
   if (plan->smem_bytes > 48 * 1024 && configured < plan->smem_bytes) {
     ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
     configured = plan->smem_bytes;
   }
-  ED_LAUNCH(kern, n_launch, THREADS, plan->smem_bytes, P, reinterpret_cast<const VecT*>(x), reinterpret_cast<VecT*>(out), partials);
+  ED_LAUNCH(kern, n_launch, U1_THREADS, plan->smem_bytes, P, reinterpret_cast<const VecT*>(x), reinterpret_cast<VecT*>(out), partials);
+}
+
+template <typename VecT, typename IdxT>
+static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
+  const int rows_per_thread = (int)((P.tile_cap + U1_THREADS - 1) / U1_THREADS);
+  if (rows_per_thread <= 2) launch_u1_r<VecT, IdxT, 2>(plan, P, n_launch, x, out, partials);
+  else if (rows_per_thread <= 7) launch_u1_r<VecT, IdxT, 7>(plan, P, n_launch, x, out, partials);
+  else if constexpr (sizeof(VecT) == 8) launch_u1_r<VecT, IdxT, 13>(plan, P, n_launch, x, out, partials);
+  else throw EdError(ED_ERR_INTERNAL, "u1 tile too large for complex vectors");
 }
 
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
@@ -460,7 +652,7 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
     if (plan->partials.n < (size_t)2 * plan->n_tiles) plan->partials.alloc((size_t)2 * plan->n_tiles);
     partials = plan->partials.p;
   }
-  const bool w32 = P.n_bits <= 32;
+  const bool w32 = plan->idx32;
   if (dtype == ED_F64) {
     if (w32) launch_u1<double, uint32_t>(plan, P, n_launch, x, out, partials); else launch_u1<double, uint64_t>(plan, P, n_launch, x, out, partials);
   } else {

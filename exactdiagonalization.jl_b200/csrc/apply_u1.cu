@@ -94,8 +94,179 @@ __device__ __forceinline__ void vec_fma(c128& acc, double a, c128 v) { acc.re = 
 __device__ __forceinline__ double vec_add(double a, double b) { return a + b; }
 __device__ __forceinline__ c128 vec_add(c128 a, c128 b) { return cadd(a, b); }
 
-// One CTA = one tile; every thread owns R rows (i = tid + r*THREADS) whose accumulators stay in registers, so
-// every bond / slot loop has R independent loads in flight per thread (the kernel is latency-bound otherwise).
+// Per-tile state handed from the prologue to the slab body.
+template <typename VecT, typename IdxT>
+struct U1Tile {
+  VecT* xs;
+  const double* hh_amp; const IdxT* hh_base; int n_hh;
+  const double* mx_amp; const IdxT* mx_base; const uint32_t* mx_toff; int n_mx;
+  const double* mq_coef; const uint32_t* mq_bit; int n_mq;
+  const double* s_dval;
+  uint32_t lofs, gofs, size;
+  int p_low;
+  IdxT base;
+  double d_tile;
+};
+
+// Slab body.  Slab r holds rows i = tid + r*THREADS.  NF = number of COMPLETE slabs of this tile (compile time:
+// constant offsets, no predicates, NF+1 independent loads in flight per thread and bond).  The last, partial slab is
+// addressed through the clamped per-thread index `it`, so every load stays in bounds; only its store is predicated.
+template <typename VecT, typename IdxT, int THREADS, int NF>
+__device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<VecT, IdxT>& T, const VecT* __restrict__ x,
+                                             VecT* __restrict__ y, bool want_dot, double& dre, double& dim_) {
+  constexpr int CH = sizeof(VecT) == 8 ? 6 : 3;   // loads issued back to back before their FMAs (register budget)
+  const int tid = threadIdx.x;
+  VecT* xs = T.xs;
+  const uint32_t size = T.size;
+  const uint32_t i_tail = tid + NF * THREADS;
+  const bool tail_ok = i_tail < size;
+  const uint32_t it = tail_ok ? i_tail : size - 1;
+  VecT acc[NF > 0 ? NF : 1];
+  VecT acc_t;
+  // diagonal
+  {
+    const uint8_t* dc = P.dcode + T.lofs;
+    const double* dl = P.dlow + T.lofs;
+    double dd[NF > 0 ? NF : 1];
+    double dt = T.d_tile;
+    if (P.diag_mode == 1) {
+      uint32_t code[NF > 0 ? NF : 1];
+#pragma unroll
+      for (int r = 0; r < NF; ++r) code[r] = __ldg(dc + tid + r * THREADS);
+      const uint32_t ct = __ldg(dc + it);
+#pragma unroll
+      for (int r = 0; r < NF; ++r) dd[r] = T.d_tile + T.s_dval[code[r]];
+      dt += T.s_dval[ct];
+    } else if (P.diag_mode == 2) {
+#pragma unroll
+      for (int r = 0; r < NF; ++r) dd[r] = T.d_tile + __ldg(dl + tid + r * THREADS);
+      dt += __ldg(dl + it);
+    } else {
+#pragma unroll
+      for (int r = 0; r < NF; ++r) dd[r] = T.d_tile;
+    }
+    if (T.n_mq) {
+      const uint16_t* lw = P.lowword + T.lofs;
+#pragma unroll
+      for (int r = 0; r <= NF; ++r) {
+        const uint32_t low = __ldg(lw + (r < NF ? tid + r * THREADS : it));
+        double d = 0.0;
+        for (int e = 0; e < T.n_mq; ++e) d += ((low >> T.mq_bit[e]) & 1u) ? T.mq_coef[e] : 0.0;
+        if (r < NF) dd[r] += d; else dt += d;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NF; ++r) acc[r] = vec_scale<VecT>(dd[r], xs[tid + r * THREADS]);
+    acc_t = vec_scale<VecT>(dt, xs[it]);
+  }
+  // bonds inside the high bits: same local index in another tile -> coalesced streams
+#pragma unroll 1
+  for (int e = 0; e < T.n_hh; ++e) {
+    const double a = T.hh_amp[e];
+    const VecT* xe = x + T.hh_base[e];
+    const VecT* xt = xe + tid;
+    const VecT vt = ldg_val(xe + it);
+#pragma unroll
+    for (int r0 = 0; r0 < NF; r0 += CH) {
+      VecT v[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) v[c] = ldg_val(xt + (r0 + c) * THREADS);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+    }
+    vec_fma(acc_t, a, vt);
+  }
+  // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers
+#pragma unroll 1
+  for (int c = 0; c < P.n_ll; ++c) {
+    const uint8_t* cnt = P.ell_cnt[c] + T.gofs;
+    int nmax = (int)__ldg(cnt + (it >> 5));
+#pragma unroll
+    for (int r = 0; r < NF; ++r) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // warp-uniform
+    const uint16_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
+    const double a = P.ll_amp[c];
+#pragma unroll 1
+    for (int sl = 0; sl < nmax; ++sl) {
+      const uint16_t* et = e + tid;
+      const uint32_t jt = __ldg(e + it);
+#pragma unroll
+      for (int r0 = 0; r0 < NF; r0 += CH) {
+        uint32_t j[CH];
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc)
+          if (r0 + cc < NF) j[cc] = __ldg(et + (r0 + cc) * THREADS);
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc)
+          if (r0 + cc < NF) vec_fma(acc[r0 + cc], a, xs[j[cc]]);
+      }
+      vec_fma(acc_t, a, xs[jt]);
+      e += size;
+    }
+  }
+  // bonds straddling bit k: tabulated local column inside the neighbouring tile (0xFFFF = does not fire)
+#pragma unroll 1
+  for (int e = 0; e < T.n_mx; ++e) {
+    const uint16_t* tab = P.mx_tab + T.mx_toff[e];
+    const uint16_t* tt = tab + tid;
+    const VecT* xe = x + T.mx_base[e];
+    const double a = T.mx_amp[e];
+    const uint32_t jt = __ldg(tab + it);
+    const VecT vt = jt != 0xFFFFu ? ldg_val(xe + jt) : vzero((VecT*)nullptr);
+#pragma unroll
+    for (int r0 = 0; r0 < NF; r0 += CH) {
+      uint32_t j[CH];
+      VecT v[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) j[c] = __ldg(tt + (r0 + c) * THREADS);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) v[c] = j[c] != 0xFFFFu ? ldg_val(xe + j[c]) : vzero((VecT*)nullptr);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+    }
+    vec_fma(acc_t, a, vt);
+  }
+  // store (row-owner writes)
+  const int64_t row0 = (int64_t)T.base + tid;
+  VecT* yt = y + (row0 - P.row_lo);
+  const bool whole = (int64_t)T.base >= P.row_lo && (int64_t)T.base + size <= P.row_hi;   // tile fully owned (uniform)
+#pragma unroll
+  for (int r = 0; r < NF; ++r) {
+    const int64_t row = row0 + r * THREADS;
+    if (!whole && (row < P.row_lo || row >= P.row_hi)) continue;
+    VecT out = acc[r];
+    if (P.accumulate) out = vec_add(out, yt[r * THREADS]);
+    st_val(yt + r * THREADS, out);
+    if (want_dot) dot_acc(dre, dim_, xs[tid + r * THREADS], out);
+  }
+  const int64_t row = (int64_t)T.base + i_tail;
+  if (tail_ok && (whole || (row >= P.row_lo && row < P.row_hi))) {
+    VecT* dst = y + (row - P.row_lo);
+    VecT out = acc_t;
+    if (P.accumulate) out = vec_add(out, *dst);
+    st_val(dst, out);
+    if (want_dot) dot_acc(dre, dim_, xs[i_tail], out);
+  }
+}
+
+template <typename VecT, typename IdxT, int THREADS, int R, int NF>
+struct U1Dispatch {
+  static __device__ __forceinline__ void run(int nfull, const U1Params& P, const U1Tile<VecT, IdxT>& T, const VecT* x, VecT* y,
+                                             bool want_dot, double& dre, double& dim_) {
+    if (nfull == NF) u1_tile_body<VecT, IdxT, THREADS, NF>(P, T, x, y, want_dot, dre, dim_);
+    else U1Dispatch<VecT, IdxT, THREADS, R, NF - 1>::run(nfull, P, T, x, y, want_dot, dre, dim_);
+  }
+};
+template <typename VecT, typename IdxT, int THREADS, int R>
+struct U1Dispatch<VecT, IdxT, THREADS, R, -1> {
+  static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT, IdxT>&, const VecT*, VecT*, bool, double&, double&) {}
+};
+
+// One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
 template <typename VecT, typename IdxT, int THREADS, int R>
 __global__ void __launch_bounds__(THREADS, 2)
 k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, double* __restrict__ dot_partials) {
@@ -116,7 +287,6 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
   const int p_low = P.n_set - __popc(H);
   const uint32_t lofs = P.lowofs[p_low];
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
-  const uint32_t gofs = P.grpofs[p_low];
   const IdxT base = (IdxT)P.tile_base[H];
   const int k = P.k;
 
@@ -167,110 +337,22 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
     if (lane == 0) s_counts[1] = n;
   }
   if (P.diag_mode == 1) for (int i = tid; i < 256; i += THREADS) s_dval[i] = P.dval[i];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const uint32_t i = tid + r * THREADS;
-    if (i < size) xs[i] = ldg_val(x + (base + i));
-  }
+  for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(x + (base + i));
   if (tid == 0) xs[size] = vzero((VecT*)nullptr);
   __syncthreads();
-  const int n_hh = s_counts[0];
-  const int n_mq = s_counts[1];
-  const int n_mx = P.n_mx;
-  const double d_tile = P.tile_diag[H];
 
-  // rows of this thread: i_r = tid + r*THREADS; `live` = inside the tile and inside the owned row range
-  VecT acc[R];
-  bool live[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const uint32_t i = tid + r * THREADS;
-    const int64_t row = (int64_t)base + i;
-    live[r] = i < size && row >= P.row_lo && row < P.row_hi;
-    acc[r] = vzero((VecT*)nullptr);
-  }
-  // diagonal
-  if (P.diag_mode == 1) {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (live[r]) { const uint32_t i = tid + r * THREADS; acc[r] = vec_scale<VecT>(d_tile + s_dval[__ldg(P.dcode + lofs + i)], xs[i]); }
-  } else if (P.diag_mode == 2) {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (live[r]) { const uint32_t i = tid + r * THREADS; acc[r] = vec_scale<VecT>(d_tile + __ldg(P.dlow + lofs + i), xs[i]); }
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (live[r]) acc[r] = vec_scale<VecT>(d_tile, xs[tid + r * THREADS]);
-  }
-  if (n_mq) {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (live[r]) {
-        const uint32_t i = tid + r * THREADS;
-        const uint32_t low = __ldg(P.lowword + lofs + i);
-        double d = 0.0;
-        for (int e = 0; e < n_mq; ++e) d += ((low >> mq_bit[e]) & 1u) ? mq_coef[e] : 0.0;
-        vec_fma(acc[r], d, xs[i]);
-      }
-  }
-  // bonds inside the high bits: same local index in another tile -> R coalesced streams in flight
-#pragma unroll 1
-  for (int e = 0; e < n_hh; ++e) {
-    const double a = hh_amp[e];
-    const VecT* xe = x + hh_base[e];
-    VecT v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = live[r] ? ldg_val(xe + (tid + r * THREADS)) : vzero((VecT*)nullptr);
-#pragma unroll
-    for (int r = 0; r < R; ++r) vec_fma(acc[r], a, v[r]);
-  }
-  // exchange bonds inside the low k bits: ELL table of local columns, shared-memory gathers
-#pragma unroll 1
-  for (int c = 0; c < P.n_ll; ++c) {
-    const uint8_t* cnt = P.ell_cnt[c] + gofs;
-    int nmax = 0;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (live[r]) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // uniform across the warp
-    const uint16_t* e = P.ell[c] + P.ell_ofs[c * (k + 1) + p_low] + tid;
-    const double a = P.ll_amp[c];
-#pragma unroll 1
-    for (int sl = 0; sl < nmax; ++sl) {
-      uint32_t j[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) j[r] = live[r] ? (uint32_t)__ldg(e + r * THREADS) : size;   // padding -> xs[size] == 0
-#pragma unroll
-      for (int r = 0; r < R; ++r) vec_fma(acc[r], a, xs[j[r]]);
-      e += size;
-    }
-  }
-  // bonds straddling bit k: tabulated local column inside the neighbouring tile
-#pragma unroll 1
-  for (int e = 0; e < n_mx; ++e) {
-    const uint16_t* tab = P.mx_tab + mx_toff[e] + tid;
-    const VecT* xe = x + mx_base[e];
-    const double a = mx_amp[e];
-    uint32_t j[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) j[r] = live[r] ? (uint32_t)__ldg(tab + r * THREADS) : 0xFFFFu;
-    VecT v[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = j[r] != 0xFFFFu ? ldg_val(xe + j[r]) : vzero((VecT*)nullptr);
-#pragma unroll
-    for (int r = 0; r < R; ++r) vec_fma(acc[r], a, v[r]);
-  }
+  U1Tile<VecT, IdxT> T;
+  T.xs = xs;
+  T.hh_amp = hh_amp; T.hh_base = hh_base; T.n_hh = s_counts[0];
+  T.mx_amp = mx_amp; T.mx_base = mx_base; T.mx_toff = mx_toff; T.n_mx = P.n_mx;
+  T.mq_coef = mq_coef; T.mq_bit = mq_bit; T.n_mq = s_counts[1];
+  T.s_dval = s_dval;
+  T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = base;
+  T.d_tile = P.tile_diag[H];
   double dre = 0.0, dim_ = 0.0;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    if (!live[r]) continue;
-    const uint32_t i = tid + r * THREADS;
-    VecT* dst = y + ((int64_t)base + i - P.row_lo);
-    VecT out = acc[r];
-    if (P.accumulate) out = vec_add(out, *dst);
-    st_val(dst, out);
-    if (dot_partials) dot_acc(dre, dim_, xs[i], out);
-  }
+  const int nfull = (int)((size - 1) / THREADS);              // complete slabs (uniform); slab `nfull` is the tail
+  U1Dispatch<VecT, IdxT, THREADS, R, R - 1>::run(nfull, P, T, x, y, dot_partials != nullptr, dre, dim_);
+
   if (dot_partials) {
     __shared__ double s_red[2][THREADS / 32];
     dre = warp_sum(dre);
@@ -512,10 +594,12 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
         for (uint32_t i = 0; i < size; ++i) {
           const uint32_t w = lowword[lowofs[p] + i];
           for (auto& l : kv.second) {
+            // highest bond first: the upper bits are shared by the rows of a warp, so the first slots are
+            // warp-uniform shifts (contiguous, conflict-free shared-memory reads)
             uint32_t t = (w ^ (w >> l.d)) & l.mask;
             while (t) {
-              const int q = __builtin_ctz(t);
-              t &= t - 1;
+              const int q = 31 - __builtin_clz(t);
+              t &= ~(1u << q);
               lists[i].push_back((uint16_t)lowrank[w ^ ((1u | (1u << l.d)) << q)]);
             }
           }

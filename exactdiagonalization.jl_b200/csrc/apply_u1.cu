@@ -92,6 +92,9 @@ __device__ __forceinline__ c128 vec_scale<c128>(double a, c128 v) { return make_
 __device__ __forceinline__ void vec_fma(double& acc, double a, double v) { acc = fma(a, v, acc); }
 __device__ __forceinline__ void vec_fma(c128& acc, double a, c128 v) { acc.re = fma(a, v.re, acc.re); acc.im = fma(a, v.im, acc.im); }
 __device__ __forceinline__ double vec_add(double a, double b) { return a + b; }
+// y is written once and never re-read by this kernel: streaming (evict-first) stores keep L2 for x
+__device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(c128* p, c128 v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
 __device__ __forceinline__ c128 vec_add(c128 a, c128 b) { return cadd(a, b); }
 
 // Per-tile state handed from the prologue to the slab body.
@@ -113,9 +116,9 @@ struct U1Tile {
 // addressed through the clamped per-thread index `it`, so every load stays in bounds; only its store is predicated.
 template <typename VecT, typename IdxT, int THREADS, int NF>
 __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<VecT, IdxT>& T, const VecT* __restrict__ x,
-                                             VecT* __restrict__ y, bool want_dot, double& dre, double& dim_) {
+                                             VecT* __restrict__ y, bool want_dot, double& dre, double& dim_, int slab0) {
   constexpr int CH = sizeof(VecT) == 8 ? 6 : 3;   // loads issued back to back before their FMAs (register budget)
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x + slab0 * THREADS;   // local row of slab 0 of this pass
   VecT* xs = T.xs;
   const uint32_t size = T.size;
   const uint32_t i_tail = tid + NF * THREADS;
@@ -240,7 +243,7 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     if (!whole && (row < P.row_lo || row >= P.row_hi)) continue;
     VecT out = acc[r];
     if (P.accumulate) out = vec_add(out, yt[r * THREADS]);
-    st_val(yt + r * THREADS, out);
+    st_stream(yt + r * THREADS, out);
     if (want_dot) dot_acc(dre, dim_, xs[tid + r * THREADS], out);
   }
   const int64_t row = (int64_t)T.base + i_tail;
@@ -248,7 +251,7 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     VecT* dst = y + (row - P.row_lo);
     VecT out = acc_t;
     if (P.accumulate) out = vec_add(out, *dst);
-    st_val(dst, out);
+    st_stream(dst, out);
     if (want_dot) dot_acc(dre, dim_, xs[i_tail], out);
   }
 }
@@ -256,19 +259,19 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
 template <typename VecT, typename IdxT, int THREADS, int R, int NF>
 struct U1Dispatch {
   static __device__ __forceinline__ void run(int nfull, const U1Params& P, const U1Tile<VecT, IdxT>& T, const VecT* x, VecT* y,
-                                             bool want_dot, double& dre, double& dim_) {
-    if (nfull == NF) u1_tile_body<VecT, IdxT, THREADS, NF>(P, T, x, y, want_dot, dre, dim_);
-    else U1Dispatch<VecT, IdxT, THREADS, R, NF - 1>::run(nfull, P, T, x, y, want_dot, dre, dim_);
+                                             bool want_dot, double& dre, double& dim_, int slab0) {
+    if (nfull == NF) u1_tile_body<VecT, IdxT, THREADS, NF>(P, T, x, y, want_dot, dre, dim_, slab0);
+    else U1Dispatch<VecT, IdxT, THREADS, R, NF - 1>::run(nfull, P, T, x, y, want_dot, dre, dim_, slab0);
   }
 };
 template <typename VecT, typename IdxT, int THREADS, int R>
 struct U1Dispatch<VecT, IdxT, THREADS, R, -1> {
-  static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT, IdxT>&, const VecT*, VecT*, bool, double&, double&) {}
+  static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT, IdxT>&, const VecT*, VecT*, bool, double&, double&, int) {}
 };
 
 // One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
 template <typename VecT, typename IdxT, int THREADS, int R>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
 k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
@@ -350,8 +353,13 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
   T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = base;
   T.d_tile = P.tile_diag[H];
   double dre = 0.0, dim_ = 0.0;
-  const int nfull = (int)((size - 1) / THREADS);              // complete slabs (uniform); slab `nfull` is the tail
-  U1Dispatch<VecT, IdxT, THREADS, R, R - 1>::run(nfull, P, T, x, y, dot_partials != nullptr, dre, dim_);
+  // passes of at most R slabs (R accumulators per thread stay in registers); all slabs but the very last are complete
+  const int n_slab = (int)((size + THREADS - 1) / THREADS);
+#pragma unroll 1
+  for (int s0 = 0; s0 < n_slab; s0 += R) {
+    const int nfull = min(R, n_slab - s0) - 1;
+    U1Dispatch<VecT, IdxT, THREADS, R, R - 1>::run(nfull, P, T, x, y, dot_partials != nullptr, dre, dim_, s0);
+  }
 
   if (dot_partials) {
     __shared__ double s_red[2][THREADS / 32];
@@ -450,14 +458,14 @@ uint64_t binom_u64(int n, int k) {
 }
 
 int choose_k(int n_bits, int vec_bytes) {
-  int k = std::min(16, std::max(4, n_bits - 11));
+  int k = std::min(15, std::max(4, n_bits - 10));   // k = 15 measured best on B200 (L=32: k=14 11.4 ms, k=15 9.1 ms, k=16 12.2 ms)
   k = std::min(k, n_bits);
   if (const char* e = getenv("EDCUDA_U1_K")) {
     int v = atoi(e);
     if (v >= 1 && v <= 16) k = std::min(v, n_bits);
   }
-  // x tile must leave room for two CTAs per SM (<= 104 KB) and at most 13 register-resident rows per thread
-  while (k > 1 && (binom_u64(k, k / 2) * (uint64_t)vec_bytes > 104 * 1024 || binom_u64(k, k / 2) > (uint64_t)(vec_bytes == 8 ? 13 : 7) * 512)) --k;
+  // x tile must leave room for two CTAs per SM: <= 104 KB
+  while (k > 1 && binom_u64(k, k / 2) * (uint64_t)vec_bytes > 104 * 1024) --k;
   return k;
 }
 
@@ -693,24 +701,21 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side) {
 
 constexpr int U1_THREADS = 512;
 
-template <typename VecT, typename IdxT, int R>
+template <typename VecT, typename IdxT, int R, int THREADS = U1_THREADS>
 static void launch_u1_r(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
-  auto kern = k2_apply_u1<VecT, IdxT, U1_THREADS, R>;
+  auto kern = k2_apply_u1<VecT, IdxT, THREADS, R>;
   static thread_local size_t configured = 0;
   if (plan->smem_bytes > 48 * 1024 && configured < plan->smem_bytes) {
     ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
     configured = plan->smem_bytes;
   }
-  ED_LAUNCH(kern, n_launch, U1_THREADS, plan->smem_bytes, P, reinterpret_cast<const VecT*>(x), reinterpret_cast<VecT*>(out), partials);
+  ED_LAUNCH(kern, n_launch, THREADS, plan->smem_bytes, P, reinterpret_cast<const VecT*>(x), reinterpret_cast<VecT*>(out), partials);
 }
 
 template <typename VecT, typename IdxT>
 static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
-  const int rows_per_thread = (int)((P.tile_cap + U1_THREADS - 1) / U1_THREADS);
-  if (rows_per_thread <= 2) launch_u1_r<VecT, IdxT, 2>(plan, P, n_launch, x, out, partials);
-  else if (rows_per_thread <= 7) launch_u1_r<VecT, IdxT, 7>(plan, P, n_launch, x, out, partials);
-  else if constexpr (sizeof(VecT) == 8) launch_u1_r<VecT, IdxT, 13>(plan, P, n_launch, x, out, partials);
-  else throw EdError(ED_ERR_INTERNAL, "u1 tile too large for complex vectors");
+  if constexpr (sizeof(VecT) == 8) launch_u1_r<VecT, IdxT, 13>(plan, P, n_launch, x, out, partials);
+  else launch_u1_r<VecT, IdxT, 7>(plan, P, n_launch, x, out, partials);
 }
 
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {

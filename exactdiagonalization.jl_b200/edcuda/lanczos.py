@@ -68,30 +68,24 @@ def split_rows(dim: int, world: int):
     return [(int(offs[r]), int(offs[r + 1])) for r in range(world)]
 
 
-class ShardedMatvec:
-    """Row-sharded y = H x over torch.distributed: x shards are all-gathered (NCCL over NVLink on GPUs),
-    then every rank applies its rows.  `opr` is this rank's representation (set_rows is called here)."""
+class RowSharding:
+    """Contiguous row shards of a length-`dim` vector over `world` ranks and the all-gather that rebuilds the full
+    vector (device agnostic: NCCL on GPUs, gloo in the CPU tests).  Ragged shards are padded to the largest one
+    for the collective and compacted afterwards."""
 
-    def __init__(self, opr, rank: int, world: int, dtype=None, group=None):
+    def __init__(self, dim: int, rank: int, world: int, t_dtype, device, group=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
-        self.opr, self.rank, self.world, self.group = opr, rank, world, group
-        self.dim = opr.dimension
-        self.ranges = split_rows(self.dim, world)
+        self.dim, self.rank, self.world, self.group = dim, rank, world, group
+        self.ranges = split_rows(dim, world)
         self.lo, self.hi = self.ranges[rank]
-        opr.set_rows(self.lo, self.hi)
-        self.np_dtype = np.dtype(dtype or (np.complex128 if opr.is_complex else np.float64))
-        self.t_dtype = torch.complex128 if self.np_dtype == np.complex128 else torch.float64
-        self.code = ED_C128 if self.np_dtype == np.complex128 else ED_F64
-        self.dev = torch.device("cuda", torch.cuda.current_device())
         self.max_rows = max(h - l for l, h in self.ranges)
         self.uniform = all(h - l == self.max_rows for l, h in self.ranges)
-        # full-length gather target; with ragged shards every rank pads to max_rows and the pieces are compacted
-        self.x_full = torch.zeros(self.dim, dtype=self.t_dtype, device=self.dev)
+        self.x_full = torch.zeros(dim, dtype=t_dtype, device=device)
         if not self.uniform:
-            self.x_pad = torch.zeros(self.max_rows * world, dtype=self.t_dtype, device=self.dev)
-            self.send = torch.zeros(self.max_rows, dtype=self.t_dtype, device=self.dev)
+            self.x_pad = torch.zeros(self.max_rows * world, dtype=t_dtype, device=device)
+            self.send = torch.zeros(self.max_rows, dtype=t_dtype, device=device)
 
     def gather(self, x_local):
         """all-gather the rank-local rows into the full-length vector."""
@@ -106,6 +100,33 @@ class ShardedMatvec:
             for r, (l, h) in enumerate(self.ranges):
                 self.x_full[l:h].copy_(self.x_pad[r * self.max_rows: r * self.max_rows + (h - l)])
         return self.x_full
+
+
+class ShardedMatvec:
+    """Row-sharded y = H x over torch.distributed: x shards are all-gathered (NCCL over NVLink on GPUs),
+    then every rank applies its rows.  `opr` is this rank's representation (set_rows is called here)."""
+
+    def __init__(self, opr, rank: int, world: int, dtype=None, group=None):
+        import torch
+        self.torch = torch
+        self.opr, self.rank, self.world, self.group = opr, rank, world, group
+        self.dim = opr.dimension
+        self.np_dtype = np.dtype(dtype or (np.complex128 if opr.is_complex else np.float64))
+        self.t_dtype = torch.complex128 if self.np_dtype == np.complex128 else torch.float64
+        self.code = ED_C128 if self.np_dtype == np.complex128 else ED_F64
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.sharding = RowSharding(self.dim, rank, world, self.t_dtype, self.dev, group)
+        self.dist = self.sharding.dist
+        self.ranges = self.sharding.ranges
+        self.lo, self.hi = self.sharding.lo, self.sharding.hi
+        opr.set_rows(self.lo, self.hi)
+
+    @property
+    def x_full(self):
+        return self.sharding.x_full
+
+    def gather(self, x_local):
+        return self.sharding.gather(x_local)
 
     def apply_local(self, y_local, x_full, dot_out=None):
         torch = self.torch

@@ -168,6 +168,8 @@ def main():
     ap.add_argument("--impl", default="edcuda")
     ap.add_argument("--workload", default="xxz_chain_L32_sz0")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+                    help="N>1: how remote rows of x reach a rank: peer loads over NVLink inside the kernel (p2p) or an NCCL all-gather per matvec")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -181,7 +183,7 @@ def main():
     import numpy as np
     import torch
     import edcuda as ed
-    from edcuda.lanczos import ShardedMatvec
+    from edcuda.lanczos import P2PShardedMatvec, ShardedMatvec
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,10 +204,11 @@ def main():
     hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
     dim = hsr.dimension
     opr = ed.represent(hsr, h).set_kernel(args.kernel)
-    mv = ShardedMatvec(opr, rank, world, np.float64)
+    p2p = world > 1 and args.exchange == "p2p" and args.kernel == 0
+    mv = P2PShardedMatvec(opr, rank, world, np.float64, n_buffers=1) if p2p else ShardedMatvec(opr, rank, world, np.float64)
     n_local = mv.hi - mv.lo
     # synthetic input: Philox normal vector keyed by the global row index (shard-count independent)
-    x_local = torch.empty(n_local, dtype=torch.float64, device=dev)
+    x_local = mv.x_buffer(0) if p2p else torch.empty(n_local, dtype=torch.float64, device=dev)
     y_local = torch.zeros(n_local, dtype=torch.float64, device=dev)
     import ctypes as C
     check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
@@ -220,7 +223,11 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        mv.matvec(y_local, x_local)
+        if p2p:
+            mv.fence()               # x changed (in a solver): peers may read it only after this stream-ordered barrier
+            mv.matvec(y_local, 0)
+        else:
+            mv.matvec(y_local, x_local)
 
     for _ in range(args.warmup):
         step()
@@ -233,6 +240,12 @@ def main():
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
     for i in range(args.steps):
+        if p2p:
+            mv.fence()
+            kev[i][0].record()
+            mv.matvec(y_local, 0)
+            kev[i][1].record()
+            continue
         if world > 1:
             xf = mv.gather(x_local)
         else:
@@ -281,13 +294,17 @@ def main():
             xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
             yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
             xh.copy_(x_local)
-            xd = torch.empty_like(x_local)
+            xd = x_local if p2p else torch.empty_like(x_local)
             e_steps = max(2, min(args.steps, 5))
             barrier()
             t0 = time.perf_counter()
             for _ in range(e_steps):
                 xd.copy_(xh, non_blocking=True)
-                mv.matvec(y_local, xd)
+                if p2p:
+                    mv.fence()
+                    mv.matvec(y_local, 0)
+                else:
+                    mv.matvec(y_local, xd)
                 yh.copy_(y_local, non_blocking=True)
                 torch.cuda.synchronize()
             barrier()
@@ -296,7 +313,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt[0])
             e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(dim * 8),
-                   "ms_per_step": dt * 1e3, "api": "ShardedMatvec.matvec with per-rank pinned host shards (H2D + all-gather + ed_apply_async + D2H)"}
+                   "ms_per_step": dt * 1e3, "api": ("P2PShardedMatvec" if p2p else "ShardedMatvec") + ".matvec with per-rank pinned host shards (H2D + exchange + ed_apply_async + D2H)"}
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -309,7 +326,8 @@ def main():
             "gnnz_per_s": nnz_eff(n, n_bonds) * value / 1e9,
             "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": dim, "n_terms": len(h.terms),
                        "rows_per_gpu": n_local, "sharding": "rows" if world > 1 else "none",
-                       "exchange": "nccl all_gather of x per matvec" if world > 1 else "none",
+                       "exchange": ("none" if world == 1 else "peer loads of far-bond tiles over NVLink inside the kernel (CUDA IPC), "
+                                    "stream-ordered NCCL fence per matvec" if p2p else "nccl all_gather of x per matvec"),
                        "l2": "inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (dim * 8 / 1e9),
                        "kernel": "generic term-walk" if args.kernel == 1 else "auto",
                        "checksum_x_dot_Hx": checksum},
@@ -323,6 +341,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line))
+    if p2p:
+        mv.close()
     if world > 1:
         dist.destroy_process_group()
 

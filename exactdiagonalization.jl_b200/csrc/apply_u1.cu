@@ -33,6 +33,7 @@ void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
 #define U1_MAX_HH 192
 #define U1_MAX_MX 64
 #define U1_MAX_MQ 64
+#define ED_MAX_SEG 16
 
 // Everything that depends only on the LOW k bits of a row is tabulated once per plan (tables live in L2):
 //   dcode / dval   diagonal of the low-bit terms (u8 code -> value)
@@ -62,7 +63,18 @@ struct U1Params {
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
+  // x as up to ED_MAX_SEG contiguous, tile-aligned segments (local memory or peer GPUs' memory mapped over NVLink)
+  int n_seg;
+  int64_t seg_lo[ED_MAX_SEG + 1];
+  const void* seg_ptr[ED_MAX_SEG];
 };
+
+template <typename VecT>
+__device__ __forceinline__ const VecT* u1_seg_resolve(const U1Params& P, uint64_t idx) {
+  int s = 0;
+  while (s + 1 < P.n_seg && (int64_t)idx >= P.seg_lo[s + 1]) ++s;
+  return reinterpret_cast<const VecT*>(P.seg_ptr[s]) + ((int64_t)idx - P.seg_lo[s]);
+}
 
 struct FastU1Plan {
   bool supported = false;
@@ -98,24 +110,24 @@ __device__ __forceinline__ void st_stream(c128* p, c128 v) { __stcs(reinterpret_
 __device__ __forceinline__ c128 vec_add(c128 a, c128 b) { return cadd(a, b); }
 
 // Per-tile state handed from the prologue to the slab body.
-template <typename VecT, typename IdxT>
+template <typename VecT>
 struct U1Tile {
   VecT* xs;
-  const double* hh_amp; const IdxT* hh_base; int n_hh;
-  const double* mx_amp; const IdxT* mx_base; const uint32_t* mx_toff; int n_mx;
+  const double* hh_amp; const VecT* const* hh_ptr; int n_hh;      // neighbour tiles as resolved pointers
+  const double* mx_amp; const VecT* const* mx_ptr; const uint32_t* mx_toff; int n_mx;
   const double* mq_coef; const uint32_t* mq_bit; int n_mq;
   const double* s_dval;
   uint32_t lofs, gofs, size;
   int p_low;
-  IdxT base;
+  int64_t base;
   double d_tile;
 };
 
 // Slab body.  Slab r holds rows i = tid + r*THREADS.  NF = number of COMPLETE slabs of this tile (compile time:
 // constant offsets, no predicates, NF+1 independent loads in flight per thread and bond).  The last, partial slab is
 // addressed through the clamped per-thread index `it`, so every load stays in bounds; only its store is predicated.
-template <typename VecT, typename IdxT, int THREADS, int NF>
-__device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<VecT, IdxT>& T, const VecT* __restrict__ x,
+template <typename VecT, int THREADS, int NF>
+__device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<VecT>& T,
                                              VecT* __restrict__ y, bool want_dot, double& dre, double& dim_, int slab0) {
   constexpr int CH = sizeof(VecT) == 8 ? 6 : 3;   // loads issued back to back before their FMAs (register budget)
   const int tid = threadIdx.x + slab0 * THREADS;   // local row of slab 0 of this pass
@@ -166,7 +178,7 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
 #pragma unroll 1
   for (int e = 0; e < T.n_hh; ++e) {
     const double a = T.hh_amp[e];
-    const VecT* xe = x + T.hh_base[e];
+    const VecT* xe = T.hh_ptr[e];
     const VecT* xt = xe + tid;
     const VecT vt = ldg_val(xe + it);
 #pragma unroll
@@ -213,7 +225,7 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
   for (int e = 0; e < T.n_mx; ++e) {
     const uint16_t* tab = P.mx_tab + T.mx_toff[e];
     const uint16_t* tt = tab + tid;
-    const VecT* xe = x + T.mx_base[e];
+    const VecT* xe = T.mx_ptr[e];
     const double a = T.mx_amp[e];
     const uint32_t jt = __ldg(tab + it);
     const VecT vt = jt != 0xFFFFu ? ldg_val(xe + jt) : vzero((VecT*)nullptr);
@@ -256,32 +268,32 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
   }
 }
 
-template <typename VecT, typename IdxT, int THREADS, int R, int NF>
+template <typename VecT, int THREADS, int R, int NF>
 struct U1Dispatch {
-  static __device__ __forceinline__ void run(int nfull, const U1Params& P, const U1Tile<VecT, IdxT>& T, const VecT* x, VecT* y,
+  static __device__ __forceinline__ void run(int nfull, const U1Params& P, const U1Tile<VecT>& T, VecT* y,
                                              bool want_dot, double& dre, double& dim_, int slab0) {
-    if (nfull == NF) u1_tile_body<VecT, IdxT, THREADS, NF>(P, T, x, y, want_dot, dre, dim_, slab0);
-    else U1Dispatch<VecT, IdxT, THREADS, R, NF - 1>::run(nfull, P, T, x, y, want_dot, dre, dim_, slab0);
+    if (nfull == NF) u1_tile_body<VecT, THREADS, NF>(P, T, y, want_dot, dre, dim_, slab0);
+    else U1Dispatch<VecT, THREADS, R, NF - 1>::run(nfull, P, T, y, want_dot, dre, dim_, slab0);
   }
 };
-template <typename VecT, typename IdxT, int THREADS, int R>
-struct U1Dispatch<VecT, IdxT, THREADS, R, -1> {
-  static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT, IdxT>&, const VecT*, VecT*, bool, double&, double&, int) {}
+template <typename VecT, int THREADS, int R>
+struct U1Dispatch<VecT, THREADS, R, -1> {
+  static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT>&, VecT*, bool, double&, double&, int) {}
 };
 
 // One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
-template <typename VecT, typename IdxT, int THREADS, int R>
-__global__ void __launch_bounds__(THREADS, THREADS == 1024 ? 1 : 2)
-k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, double* __restrict__ dot_partials) {
+template <typename VecT, int THREADS, int R>
+__global__ void __launch_bounds__(THREADS, 2)
+k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
   double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 1);
   double* mx_amp = hh_amp + U1_MAX_HH;
   double* mq_coef = mx_amp + U1_MAX_MX;
   double* s_dval = mq_coef + U1_MAX_MQ;                                // 256
-  IdxT* hh_base = reinterpret_cast<IdxT*>(s_dval + 256);
-  IdxT* mx_base = hh_base + U1_MAX_HH;
-  uint32_t* mx_toff = reinterpret_cast<uint32_t*>(mx_base + U1_MAX_MX);
+  const VecT** hh_ptr = reinterpret_cast<const VecT**>(s_dval + 256);
+  const VecT** mx_ptr = hh_ptr + U1_MAX_HH;
+  uint32_t* mx_toff = reinterpret_cast<uint32_t*>(mx_ptr + U1_MAX_MX);
   uint32_t* mq_bit = mx_toff + U1_MAX_MX;
   __shared__ int s_counts[2];
 
@@ -290,7 +302,7 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
   const int p_low = P.n_set - __popc(H);
   const uint32_t lofs = P.lowofs[p_low];
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
-  const IdxT base = (IdxT)P.tile_base[H];
+  const uint64_t base = P.tile_base[H];
   const int k = P.k;
 
   // ---- prologue: per-tile bond lists (deterministic ballot compaction), x tile --------------------------
@@ -308,7 +320,7 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (fire) {
         const int slot = n + __popc(m & ((1u << tid) - 1u));
-        hh_base[slot] = (IdxT)P.tile_base[H2];
+        hh_ptr[slot] = u1_seg_resolve<VecT>(P, P.tile_base[H2]);
         hh_amp[slot] = P.hh_amp[b];
       }
       n += __popc(m);
@@ -319,7 +331,7 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
     for (int b = lane; b < P.n_mx; b += 32) {
       const int q = P.mx_q[b];
       const uint32_t hbit = (H >> q) & 1u;
-      mx_base[b] = (IdxT)P.tile_base[H ^ (1u << q)];
+      mx_ptr[b] = u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)]);
       mx_amp[b] = P.mx_amp[b];
       mx_toff[b] = ((uint32_t)(2 * b + hbit) << k) + lofs;
     }
@@ -340,17 +352,20 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
     if (lane == 0) s_counts[1] = n;
   }
   if (P.diag_mode == 1) for (int i = tid; i < 256; i += THREADS) s_dval[i] = P.dval[i];
-  for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(x + (base + i));
+  {
+    const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
+    for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
+  }
   if (tid == 0) xs[size] = vzero((VecT*)nullptr);
   __syncthreads();
 
-  U1Tile<VecT, IdxT> T;
+  U1Tile<VecT> T;
   T.xs = xs;
-  T.hh_amp = hh_amp; T.hh_base = hh_base; T.n_hh = s_counts[0];
-  T.mx_amp = mx_amp; T.mx_base = mx_base; T.mx_toff = mx_toff; T.n_mx = P.n_mx;
+  T.hh_amp = hh_amp; T.hh_ptr = hh_ptr; T.n_hh = s_counts[0];
+  T.mx_amp = mx_amp; T.mx_ptr = mx_ptr; T.mx_toff = mx_toff; T.n_mx = P.n_mx;
   T.mq_coef = mq_coef; T.mq_bit = mq_bit; T.n_mq = s_counts[1];
   T.s_dval = s_dval;
-  T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = base;
+  T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = (int64_t)base;
   T.d_tile = P.tile_diag[H];
   double dre = 0.0, dim_ = 0.0;
   // passes of at most R slabs (R accumulators per thread stay in registers); all slabs but the very last are complete
@@ -358,7 +373,7 @@ k2_apply_u1(const U1Params P, const VecT* __restrict__ x, VecT* __restrict__ y, 
 #pragma unroll 1
   for (int s0 = 0; s0 < n_slab; s0 += R) {
     const int nfull = min(R, n_slab - s0) - 1;
-    U1Dispatch<VecT, IdxT, THREADS, R, R - 1>::run(nfull, P, T, x, y, dot_partials != nullptr, dre, dim_, s0);
+    U1Dispatch<VecT, THREADS, R, R - 1>::run(nfull, P, T, y, dot_partials != nullptr, dre, dim_, s0);
   }
 
   if (dot_partials) {
@@ -676,9 +691,8 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   for (int c = 0; c < P.n_ll; ++c) { P.ell[c] = plan->ell[c].p; P.ell_cnt[c] = plan->ell_cnt[c].p; }
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
   P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
-  const size_t idx_bytes = plan->idx32 ? 4 : 8;
   plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
-                     (U1_MAX_HH + U1_MAX_MX) * idx_bytes + (U1_MAX_MX + U1_MAX_MQ) * 4;
+                     (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4;
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
   plan->supported = true;
   return plan;
@@ -701,21 +715,33 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side) {
 
 constexpr int U1_THREADS = 512;
 
-template <typename VecT, typename IdxT, int R, int THREADS = U1_THREADS>
-static void launch_u1_r(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
-  auto kern = k2_apply_u1<VecT, IdxT, THREADS, R>;
+template <typename VecT, int R>
+static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, void* out, double* partials) {
+  auto kern = k2_apply_u1<VecT, U1_THREADS, R>;
   static thread_local size_t configured = 0;
   if (plan->smem_bytes > 48 * 1024 && configured < plan->smem_bytes) {
     ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
     configured = plan->smem_bytes;
   }
-  ED_LAUNCH(kern, n_launch, THREADS, plan->smem_bytes, P, reinterpret_cast<const VecT*>(x), reinterpret_cast<VecT*>(out), partials);
+  ED_LAUNCH(kern, n_launch, U1_THREADS, plan->smem_bytes, P, reinterpret_cast<VecT*>(out), partials);
 }
 
-template <typename VecT, typename IdxT>
-static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, const void* x, void* out, double* partials) {
-  if constexpr (sizeof(VecT) == 8) launch_u1_r<VecT, IdxT, 13>(plan, P, n_launch, x, out, partials);
-  else launch_u1_r<VecT, IdxT, 7>(plan, P, n_launch, x, out, partials);
+// contiguous, count-balanced row ranges whose boundaries fall on tile boundaries (so every tile, and therefore every
+// neighbour stream, lives in exactly one x segment)
+void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi) {
+  FastU1Plan* plan = get_plan(o, dtype);
+  const int64_t dim = o->dim;
+  auto snap = [&](int64_t target) -> int64_t {
+    if (target <= 0) return 0;
+    if (target >= dim) return dim;
+    if (!plan->supported) return target;
+    auto it = std::lower_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)target);
+    int64_t up = it == plan->h_base.end() ? dim : (int64_t)*it;
+    int64_t down = it == plan->h_base.begin() ? 0 : (int64_t)*(it - 1);
+    return (up - target <= target - down) ? up : down;
+  };
+  *lo = snap(dim / world * rank + std::min<int64_t>(rank, dim % world));
+  *hi = snap(dim / world * (rank + 1) + std::min<int64_t>(rank + 1, dim % world));
 }
 
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
@@ -726,6 +752,23 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   P.row_lo = o->row_lo;
   P.row_hi = o->row_hi;
   P.accumulate = accumulate;
+  if (o->x_seg_ptr.empty()) {
+    ED_REQUIRE(x != nullptr, ED_ERR_ARGUMENT, "null input vector");
+    P.n_seg = 1;
+    P.seg_lo[0] = 0; P.seg_lo[1] = o->dim;
+    P.seg_ptr[0] = x;
+  } else {
+    P.n_seg = (int)o->x_seg_ptr.size();
+    for (int s = 0; s <= P.n_seg; ++s) P.seg_lo[s] = o->x_seg_lo[s];
+    for (int s = 0; s < P.n_seg; ++s) {
+      P.seg_ptr[s] = o->x_seg_ptr[s];
+      if (s > 0) {
+        const uint64_t b = (uint64_t)o->x_seg_lo[s];
+        ED_REQUIRE(b == (uint64_t)o->dim || std::binary_search(plan->h_base.begin(), plan->h_base.end(), b), ED_ERR_ARGUMENT,
+                   "x segment boundaries must fall on tile boundaries (use ed_oprep_suggest_rows)");
+      }
+    }
+  }
   // tiles overlapping the owned rows [row_lo, row_hi)
   int first = (int)(std::upper_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)std::max<int64_t>(o->row_lo, 0)) - plan->h_base.begin()) - 1;
   first = std::max(first, 0);
@@ -741,11 +784,7 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
     if (plan->partials.n < (size_t)2 * plan->n_tiles) plan->partials.alloc((size_t)2 * plan->n_tiles);
     partials = plan->partials.p;
   }
-  const bool w32 = plan->idx32;
-  if (dtype == ED_F64) {
-    if (w32) launch_u1<double, uint32_t>(plan, P, n_launch, x, out, partials); else launch_u1<double, uint64_t>(plan, P, n_launch, x, out, partials);
-  } else {
-    if (w32) launch_u1<c128, uint32_t>(plan, P, n_launch, x, out, partials); else launch_u1<c128, uint64_t>(plan, P, n_launch, x, out, partials);
-  }
+  if (dtype == ED_F64) launch_u1<double, 13>(plan, P, n_launch, out, partials);
+  else launch_u1<c128, 7>(plan, P, n_launch, out, partials);
   if (alpha_dot) ed_reduce_pairs(partials, n_launch, alpha_dot);
 }

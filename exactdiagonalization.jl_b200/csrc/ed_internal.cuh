@@ -261,6 +261,9 @@ struct ed_oprep {
   int64_t dim = 0;
   int64_t row_lo = 0, row_hi = 0;
   int kernel_choice = 0;
+  // x handed over as contiguous segments (multi-GPU: peers' shards mapped over NVLink); empty = plain pointer
+  std::vector<int64_t> x_seg_lo;
+  std::vector<const void*> x_seg_ptr;
   TermsDev terms_left, terms_right;
   bool terms_ready = false;
   std::shared_ptr<FastU1Plan> u1plan, u1plan_c;  // f64 / c128 vectors
@@ -279,6 +282,7 @@ void ed_apply_generic(ed_oprep* o, void* out, const void* x, int dtype, int side
 bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side);                                   // apply_u1.cu
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate,
                  double* alpha_dot);
+void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
                       double* alpha_dot);                                                       // reduced.cu (K6)
 void ed_sparse_assemble(ed_oprep* o, double tol);                                               // sparse.cu (K3/K4)

@@ -107,4 +107,45 @@ int ed_set_stream(void* cuda_stream, int32_t enable) {
 
 int64_t ed_kernel_launch_count(void) { return g_launch_count.load(); }
 
+// ---- device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink) ----
+int ed_device_malloc(int64_t bytes, void** ptr) {
+  ED_TRY
+  ED_REQUIRE(ptr && bytes >= 0, ED_ERR_ARGUMENT, "bad arguments");
+  ed_require_device();
+  *ptr = nullptr;
+  if (bytes > 0) ED_CUDA(cudaMalloc(ptr, (size_t)bytes));
+  ED_CATCH
+}
+
+int ed_device_free(void* ptr) {
+  ED_TRY
+  if (ptr) ED_CUDA(cudaFree(ptr));
+  ED_CATCH
+}
+
+int ed_ipc_get_handle(void* dev_ptr, uint8_t* handle64) {
+  ED_TRY
+  ED_REQUIRE(dev_ptr && handle64, ED_ERR_ARGUMENT, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  ED_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+  memcpy(handle64, &h, 64);
+  ED_CATCH
+}
+
+int ed_ipc_open_handle(const uint8_t* handle64, void** ptr) {
+  ED_TRY
+  ED_REQUIRE(handle64 && ptr, ED_ERR_ARGUMENT, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  ED_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  ED_CATCH
+}
+
+int ed_ipc_close_handle(void* ptr) {
+  ED_TRY
+  if (ptr) ED_CUDA(cudaIpcCloseMemHandle(ptr));
+  ED_CATCH
+}
+
 }  // extern "C"

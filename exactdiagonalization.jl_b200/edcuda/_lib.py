@@ -58,6 +58,11 @@ SIGNATURES = {
     "ed_set_device": (C.c_int, [C.c_int]),
     "ed_set_stream": (C.c_int, [vp, i32]),
     "ed_kernel_launch_count": (i64, []),
+    "ed_device_malloc": (C.c_int, [i64, P(vp)]),
+    "ed_device_free": (C.c_int, [vp]),
+    "ed_ipc_get_handle": (C.c_int, [vp, vp]),
+    "ed_ipc_open_handle": (C.c_int, [vp, P(vp)]),
+    "ed_ipc_close_handle": (C.c_int, [vp]),
     "ed_space_create": (C.c_int, [i32, vp, vp, i32, P(vp)]),
     "ed_space_destroy": (C.c_int, [vp]),
     "ed_space_bitwidth": (C.c_int, [vp, P(i32)]),
@@ -89,6 +94,8 @@ SIGNATURES = {
     "ed_oprep_dim": (C.c_int, [vp, P(i64)]),
     "ed_oprep_dtype": (C.c_int, [vp, P(i32)]),
     "ed_oprep_set_rows": (C.c_int, [vp, i64, i64]),
+    "ed_oprep_suggest_rows": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64)]),
+    "ed_oprep_set_x_segments": (C.c_int, [vp, i32, vp, vp]),
     "ed_oprep_set_kernel": (C.c_int, [vp, i32]),
     "ed_apply": (C.c_int, [vp, vp, i64, vp, i64, i32, i32, i32]),
     "ed_apply_async": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),

@@ -142,17 +142,134 @@ class ShardedMatvec:
         return self.apply_local(y_local, self.gather(x_local), dot_out)
 
 
+class DeviceBuffer:
+    """Device memory allocated by the library (cudaMalloc) so that it can be exported to the other per-GPU
+    processes of the node through CUDA IPC; viewed as a torch tensor through __cuda_array_interface__."""
+
+    def __init__(self, n: int, np_dtype):
+        self.n, self.np_dtype = int(n), np.dtype(np_dtype)
+        p = C.c_void_p()
+        check(lib.ed_device_malloc(max(self.n, 1) * self.np_dtype.itemsize, C.byref(p)))
+        self.ptr = p.value
+        self.__cuda_array_interface__ = {"shape": (self.n,), "typestr": self.np_dtype.str, "data": (self.ptr, False),
+                                         "version": 2, "strides": None}
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def ipc_handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        check(lib.ed_ipc_get_handle(C.c_void_p(self.ptr), h))
+        return bytes(h)
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and lib is not None:
+            try:
+                lib.ed_device_free(C.c_void_p(self.ptr))
+            except Exception:
+                pass
+
+
+class P2PShardedMatvec:
+    """Row-sharded y = H x WITHOUT an all-gather: every rank keeps its rows of x in a buffer that the other ranks map
+    through CUDA IPC, and the matvec kernel pulls the few neighbour tiles it needs straight over NVLink (peer loads),
+    overlapped with its local work.  Shards are tile aligned (ed_oprep_suggest_rows).  `n_buffers` shared buffers are
+    kept so that a Lanczos loop can ping-pong between them.  Only the U(1) fast-path kernel consumes segmented inputs."""
+
+    def __init__(self, opr, rank: int, world: int, dtype=None, group=None, n_buffers: int = 2):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.opr, self.rank, self.world, self.group = opr, rank, world, group
+        self.dim = opr.dimension
+        self.np_dtype = np.dtype(dtype or (np.complex128 if opr.is_complex else np.float64))
+        self.t_dtype = torch.complex128 if self.np_dtype == np.complex128 else torch.float64
+        self.code = ED_C128 if self.np_dtype == np.complex128 else ED_F64
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.ranges = []
+        for r in range(world):
+            lo, hi = C.c_int64(), C.c_int64()
+            check(lib.ed_oprep_suggest_rows(opr._handle, self.code, world, r, C.byref(lo), C.byref(hi)))
+            self.ranges.append((lo.value, hi.value))
+        self.lo, self.hi = self.ranges[rank]
+        opr.set_rows(self.lo, self.hi)
+        n_local = self.hi - self.lo
+        self.bufs = [DeviceBuffer(n_local, self.np_dtype) for _ in range(n_buffers)]
+        self.views = [b.tensor() for b in self.bufs]
+        for v in self.views:
+            v.zero_()
+        torch.cuda.synchronize()
+        mine = [b.ipc_handle() for b in self.bufs]
+        if world > 1:
+            allh = [None] * world
+            dist.all_gather_object(allh, mine, group=group)
+        else:
+            allh = [mine]
+        self._opened = []
+        self.seg_ptr = []      # per buffer: pointer of every rank's shard as seen from this process
+        for b in range(n_buffers):
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(self.bufs[b].ptr)
+                else:
+                    p = C.c_void_p()
+                    check(lib.ed_ipc_open_handle((C.c_uint8 * 64).from_buffer_copy(allh[r][b]), C.byref(p)))
+                    self._opened.append(p.value)
+                    ptrs.append(p.value)
+            self.seg_ptr.append(ptrs)
+        self.seg_lo = (C.c_int64 * (world + 1))(*([r[0] for r in self.ranges] + [self.dim]))
+        self._token = torch.zeros(1, dtype=torch.float32, device=self.dev)
+
+    def x_buffer(self, which: int = 0):
+        """This rank's rows of shared input buffer `which` (a torch tensor; write x here)."""
+        return self.views[which]
+
+    def fence(self):
+        """Stream-ordered barrier across ranks: call after writing a shared buffer, before peers read it."""
+        if self.world > 1:
+            self.dist.all_reduce(self._token, group=self.group)
+
+    def matvec(self, y_local, which: int = 0, dot_out=None):
+        torch = self.torch
+        ptrs = (C.c_void_p * self.world)(*self.seg_ptr[which])
+        check(lib.ed_oprep_set_x_segments(self.opr._handle, self.world, self.seg_lo, ptrs))
+        check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+        try:
+            check(lib.ed_apply_async(self.opr._handle, y_local.data_ptr(), None, self.code, ED_SIDE_LEFT, 0,
+                                     dot_out.data_ptr() if dot_out is not None else None))
+        finally:
+            lib.ed_set_stream(None, 0)
+            lib.ed_oprep_set_x_segments(self.opr._handle, 0, None, None)
+        return y_local
+
+    def close(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)
+        for p in self._opened:
+            lib.ed_ipc_close_handle(C.c_void_p(p))
+        self._opened = []
+
+
 class ShardedLanczos:
     """Three-term Lanczos with unnormalised, device-resident, row-sharded Krylov vectors (see csrc/lanczos.cu).
     Per step: one all-gather (x), two scalar all-reduces (<u,Hu> and |u_next|^2); no host synchronisation."""
 
-    def __init__(self, opr, rank: int = 0, world: int = 1, dtype=None, group=None):
-        self.mv = ShardedMatvec(opr, rank, world, dtype, group)
+    def __init__(self, opr, rank: int = 0, world: int = 1, dtype=None, group=None, exchange: str = "allgather"):
+        """exchange = "allgather" (NCCL all-gather of x per step) or "p2p" (peer loads of the far tiles, no gather)."""
+        self.p2p = exchange == "p2p"
+        self.mv = P2PShardedMatvec(opr, rank, world, dtype, group) if self.p2p else ShardedMatvec(opr, rank, world, dtype, group)
         torch = self.mv.torch
         n = self.mv.hi - self.mv.lo
         self.n_local = n
         mk = lambda: torch.zeros(max(n, 1), dtype=self.mv.t_dtype, device=self.mv.dev)[:n]
-        self.u_cur, self.u_prev, self.w = mk(), mk(), mk()
+        if self.p2p:
+            self.u_cur, self.u_prev, self.w = self.mv.x_buffer(0), self.mv.x_buffer(1), mk()
+            self._cur = 0
+        else:
+            self.u_cur, self.u_prev, self.w = mk(), mk(), mk()
 
     def _ed_stream(self):
         torch = self.mv.torch
@@ -175,7 +292,13 @@ class ShardedLanczos:
         if mv.world > 1:
             dist.all_reduce(norms[0], group=mv.group)
         for j in range(n_steps):
-            mv.matvec(self.w, self.u_cur, dots[j])
+            if self.p2p:
+                # peers may read u_cur only after its owner finished writing it: the all-reduce of norms[j] above
+                # (stream ordered, issued after the update kernel) is that fence
+                mv.matvec(self.w, self._cur, dots[j])
+                self._cur ^= 1
+            else:
+                mv.matvec(self.w, self.u_cur, dots[j])
             if mv.world > 1:
                 dist.all_reduce(dots[j], group=mv.group)
             self._ed_stream()

@@ -78,6 +78,15 @@ int  ed_set_stream(void* cuda_stream, int32_t enable);
 /* total number of kernel launches issued by the library in this process (for bench accounting). */
 int64_t ed_kernel_launch_count(void);
 
+/* device buffers that the per-GPU processes of one node can map into each other (CUDA IPC, peer access over
+ * NVLink): the row-sharded matvec reads the far-bond tiles of x straight from the owning GPU instead of
+ * all-gathering the whole vector.  handle64 is a 64-byte cudaIpcMemHandle_t. */
+int ed_device_malloc(int64_t bytes, void** ptr);
+int ed_device_free(void* ptr);
+int ed_ipc_get_handle(void* dev_ptr, uint8_t* handle64);
+int ed_ipc_open_handle(const uint8_t* handle64, void** ptr);
+int ed_ipc_close_handle(void* ptr);
+
 /* ---- HilbertSpace  (HilbertSpace/hilbert_space.jl:25-41, site.jl:69-93) ------------- */
 /* n_states[i] local states on site i; qn is [sum_i n_states[i]][n_qn] row-major: the quantum
  * number tuple of every local state in site order.  Site 0 occupies the least significant
@@ -169,6 +178,14 @@ int ed_oprep_dtype(const ed_oprep* oprep, int32_t* dtype);
 /* Row-shard the representation (multi-GPU): this process owns output rows [row_lo, row_hi)
  * (0-based, half open).  x keeps the full length; out has row_hi-row_lo elements. Default: all rows. */
 int ed_oprep_set_rows(ed_oprep* oprep, int64_t row_lo, int64_t row_hi);
+/* Row range rank `rank` of `world` should own: the reference's balanced splitrange (src/util.jl:102-121) with the
+ * boundaries snapped to the fast kernel's tile boundaries, so that segmented inputs (below) are tile aligned. */
+int ed_oprep_suggest_rows(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi);
+/* Hand the input vector over as n_seg (<= 16) contiguous segments instead of one pointer: segment s holds rows
+ * [seg_lo[s], seg_lo[s+1]) at device address seg_ptr[s] (local memory or a peer GPU's buffer opened with
+ * ed_ipc_open_handle).  While set, ed_apply_async ignores its `x` argument.  n_seg = 0 clears.  Only the U(1)
+ * fast-path kernel consumes segments (ED_ERR_UNSUPPORTED otherwise); boundaries must come from ed_oprep_suggest_rows. */
+int ed_oprep_set_x_segments(ed_oprep* oprep, int32_t n_seg, const int64_t* seg_lo, const void* const* seg_ptr);
 /* Choose the kernel: 0 = automatic (fastest exact path), 1 = force the generic term-walk kernel. */
 int ed_oprep_set_kernel(ed_oprep* oprep, int32_t which);
 

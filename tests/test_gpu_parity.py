@@ -800,6 +800,8 @@ def test_sharded_lanczos_world1_matches_library_driver(gpu_ed, golden):
     ref = lanczos(ed.represent(hsr, h), 100, seed=9)
     sl = ShardedLanczos(ed.represent(hsr, h), 0, 1)
     res = sl.run(100, seed=9)
+    res_p = ShardedLanczos(ed.represent(hsr, h), 0, 1, exchange="p2p").run(100, seed=9)
+    assert np.allclose(res_p.alpha[:30], ref.alpha[:30], atol=1e-10) and abs(res_p.ritz[0] - ref.ritz[0]) < 1e-10
     assert np.allclose(res.alpha[:30], ref.alpha[:30], atol=1e-10) and np.allclose(res.beta[:30], ref.beta[:30], atol=1e-10)
     assert abs(res.ritz[0] - golden["known_answers"]["L16_E0"]) < 1e-10
 
@@ -819,7 +821,19 @@ def _nccl_worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     hs, h = ed.models.j1j2_chain(20, 0.5)
     hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
+    from edcuda.lanczos import P2PShardedMatvec
     res = ShardedLanczos(ed.represent(hsr, h), rank, world).run(120, seed=4)
+    res_p = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="p2p").run(120, seed=4)
+    pm = P2PShardedMatvec(ed.represent(hsr, h), rank, world, n_buffers=1)
+    xp = pm.x_buffer(0)
+    xp.copy_(torch.arange(pm.lo, pm.hi, dtype=torch.float64, device="cuda").sin())
+    yp = torch.zeros_like(xp)
+    pm.fence()
+    pm.matvec(yp, 0)
+    torch.cuda.synchronize()
+    yps = [None] * world
+    dist.all_gather_object(yps, yp.cpu().numpy())
+    pm.close()
     mv = ShardedMatvec(ed.represent(hsr, h), rank, world)
     x = torch.arange(mv.lo, mv.hi, dtype=torch.float64, device="cuda").sin()
     y = torch.zeros_like(x)
@@ -828,7 +842,7 @@ def _nccl_worker(rank, world, port, q):
     ys = [None] * world
     dist.all_gather_object(ys, y.cpu().numpy())
     if rank == 0:
-        q.put((res.alpha, res.beta, res.ritz, np.concatenate(ys)))
+        q.put((res.alpha, res.beta, res.ritz, np.concatenate(ys), res_p.alpha, res_p.beta, res_p.ritz, np.concatenate(yps)))
     dist.destroy_process_group()
 
 
@@ -849,7 +863,7 @@ def test_multi_gpu_row_sharding_nccl(gpu_ed):
     procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    alpha, beta, ritz, y = q.get(timeout=300)
+    alpha, beta, ritz, y, alpha_p, beta_p, ritz_p, y_p = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -864,3 +878,6 @@ def test_multi_gpu_row_sharding_nccl(gpu_ed):
     assert abs(ritz[0] + 30.0) < 1e-9        # Majumdar-Ghosh: -1.5 L
     x = np.sin(np.arange(hsr.dimension, dtype=np.float64))
     assert rel_err(y, opr * x) < TOL
+    # peer-load (no all-gather) exchange gives the same numbers
+    assert rel_err(y_p, opr * x) < TOL
+    assert np.allclose(alpha_p[:25], ref.alpha[:25], atol=1e-9) and abs(ritz_p[0] - ref.ritz[0]) < 1e-10

@@ -47,6 +47,31 @@ int ed_sm_count() {
   return cached[dev];
 }
 
+// Staging buffers for host vectors are cached per thread (the two largest are kept): a Krylov solver calling
+// mul! with host arrays would otherwise pay cudaMalloc/cudaFree of gigabytes on every call.
+namespace {
+struct StageSlot { void* p = nullptr; size_t cap = 0; bool busy = false; };
+thread_local StageSlot t_stage[2];
+void* stage_acquire(size_t nbytes) {
+  for (auto& s : t_stage)
+    if (!s.busy && s.cap >= nbytes) { s.busy = true; return s.p; }
+  for (auto& s : t_stage)
+    if (!s.busy) {
+      if (s.p) cudaFree(s.p);
+      s.p = nullptr; s.cap = 0;
+      ED_CUDA(cudaMalloc(&s.p, nbytes));
+      s.cap = nbytes; s.busy = true;
+      return s.p;
+    }
+  return nullptr;
+}
+bool stage_release(void* p) {
+  for (auto& s : t_stage)
+    if (s.p == p && s.busy) { s.busy = false; return true; }
+  return false;
+}
+}  // namespace
+
 Staged::Staged(const void* p, size_t nbytes, bool copy_in, bool copy_out) : bytes(nbytes), writeback(copy_out) {
   if (nbytes == 0 || p == nullptr) { dev = const_cast<void*>(p); return; }
   if (ed_is_device_pointer(p)) {
@@ -57,7 +82,8 @@ Staged::Staged(const void* p, size_t nbytes, bool copy_in, bool copy_out) : byte
   }
   host = const_cast<void*>(p);
   owned = true;
-  ED_CUDA(cudaMalloc(&dev, nbytes));
+  dev = stage_acquire(nbytes);
+  if (!dev) ED_CUDA(cudaMalloc(&dev, nbytes));
   if (copy_in) ED_CUDA(cudaMemcpyAsync(dev, host, nbytes, cudaMemcpyHostToDevice, ed_stream()));
 }
 
@@ -67,14 +93,17 @@ void Staged::finish() {
       ED_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ed_stream()));
       ED_CUDA(cudaStreamSynchronize(ed_stream()));
     }
-    cudaFree(dev);
+    if (!stage_release(dev)) cudaFree(dev);
     dev = nullptr;
     owned = false;
   }
 }
 
 Staged::~Staged() {
-  if (owned && dev) cudaFree(dev);
+  if (owned && dev) {
+    cudaStreamSynchronize(ed_stream());
+    if (!stage_release(dev)) cudaFree(dev);
+  }
 }
 
 extern "C" {
@@ -139,6 +168,13 @@ int ed_ipc_open_handle(const uint8_t* handle64, void** ptr) {
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   ED_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  ED_CATCH
+}
+
+int ed_release_staging(void) {
+  ED_TRY
+  for (auto& s : t_stage)
+    if (!s.busy && s.p) { cudaFree(s.p); s.p = nullptr; s.cap = 0; }
   ED_CATCH
 }
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "ed_set_device": (C.c_int, [C.c_int]),
     "ed_set_stream": (C.c_int, [vp, i32]),
     "ed_kernel_launch_count": (i64, []),
+    "ed_release_staging": (C.c_int, []),
     "ed_device_malloc": (C.c_int, [i64, P(vp)]),
     "ed_device_free": (C.c_int, [vp]),
     "ed_ipc_get_handle": (C.c_int, [vp, vp]),

@@ -75,6 +75,9 @@ int  ed_set_device(int device);
 /* enable != 0: run this thread's library work on `cuda_stream` (a cudaStream_t; NULL = the legacy default
  * stream) instead of the library's own non-blocking stream; enable == 0 restores the library stream. */
 int  ed_set_stream(void* cuda_stream, int32_t enable);
+/* host vectors are staged through device buffers that the library keeps between calls (per host thread, the two
+ * largest); this frees them. */
+int  ed_release_staging(void);
 /* total number of kernel launches issued by the library in this process (for bench accounting). */
 int64_t ed_kernel_launch_count(void);
 

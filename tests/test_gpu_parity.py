@@ -881,3 +881,41 @@ def test_multi_gpu_row_sharding_nccl(gpu_ed):
     # peer-load (no all-gather) exchange gives the same numbers
     assert rel_err(y_p, opr * x) < TOL
     assert np.allclose(alpha_p[:25], ref.alpha[:25], atol=1e-9) and abs(ritz_p[0] - ref.ritz[0]) < 1e-10
+
+
+# ------------------------------------------------------------------ config 4 at full size
+def test_triangular_6x6_full_size(gpu_ed, golden):
+    """Config 4: 6x6 triangular Heisenberg, T x| C6v, k=0 A1, Sz=0.  The parent sector has 9,075,135,300 states and is
+    never materialised; the reduced dimension must equal the Burnside count 21,029,820.  The reduced
+    matvec is checked through size-independent properties: Hermiticity <z,Hx> = conj(<x,Hz>), linearity, and a
+    sampled row against the row iterator."""
+    ed = gpu_ed
+    import torch
+    hs, h = ed.models.heisenberg_triangular(6)
+    assert len(h.terms) == 648
+    hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
+    assert hsr.dimension == 9075135300 and hsr.kind == ed.ED_BASIS_COMBINADIC
+    symops = ed.lattices.triangular_space_group_irrep(6, "A1")
+    rhsr = ed.symmetry_reduce(hsr, symops)
+    d = rhsr.dimension
+    assert d == golden["known_answers"]["tri6x6_k0A1_dim"]
+    words = rhsr.basis_list
+    assert np.all(words[1:] > words[:-1]) and int(words[0]) == (1 << 18) - 1
+    sizes = rhsr.orbit_sizes()
+    assert sizes.max() == 432 and np.all(432 % sizes == 0)
+    assert int(sizes.astype(np.int64).sum()) == hsr.dimension          # the orbits of the representatives tile the parent
+    ropr = ed.represent(rhsr, h)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(d, dtype=torch.complex128, device="cuda", generator=g)
+    z = torch.randn(d, dtype=torch.complex128, device="cuda", generator=g)
+    hx, hz, hc = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    ed.mul_b(hx, ropr, x)
+    ed.mul_b(hz, ropr, z)
+    ed.mul_b(hc, ropr, (0.5 - 2j) * x + z)
+    torch.cuda.synchronize()
+    assert abs(complex(torch.vdot(z, hx)) - complex(torch.vdot(hz, x))) < 1e-9 * float(hx.norm() * z.norm())
+    assert float((hc - ((0.5 - 2j) * hx + hz)).abs().max() / hx.abs().max()) < TOL
+    i = 12345678
+    xc = x.cpu().numpy()
+    row = sum(a * xc[j - 1] for j, a in ropr.get_row_iterator(i) if j > 0)
+    assert abs(row - complex(hx[i - 1])) < 1e-11 * abs(row)

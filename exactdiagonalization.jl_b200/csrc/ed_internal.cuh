@@ -253,6 +253,16 @@ struct RLookupDesc {
 // ------------------------------------------------------------------ operator representation
 struct FastU1Plan;  // apply_u1.cu
 
+// assembled rows kept on device for repeated matvecs (sparse.cu)
+struct CsrCache {
+  int side = 0;
+  int64_t row_lo = 0, row_hi = 0, nnz = 0;
+  bool val_complex = false;
+  DevBuf<int64_t> rowptr;   // 0-based, row_hi-row_lo+1 entries
+  DevBuf<int32_t> col;      // 0-based
+  DevBuf<double> val;       // nnz doubles or nnz (re,im) pairs
+};
+
 struct ed_oprep {
   ed_basis* basis = nullptr;    // plain representation: its basis; reduced: the parent basis
   ed_rbasis* rbasis = nullptr;  // non-null for ReducedOperatorRepresentation
@@ -267,6 +277,7 @@ struct ed_oprep {
   TermsDev terms_left, terms_right;
   bool terms_ready = false;
   std::shared_ptr<FastU1Plan> u1plan, u1plan_c;  // f64 / c128 vectors
+  std::shared_ptr<CsrCache> csr[2];               // per side, built by ed_oprep_cache_matrix
   // sparse() result kept between ed_sparse_count and ed_sparse_fetch
   DevBuf<int64_t> sp_colptr, sp_rowval;
   DevBuf<double> sp_nzval;
@@ -285,5 +296,6 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
                       double* alpha_dot);                                                       // reduced.cu (K6)
+void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot);
 void ed_sparse_assemble(ed_oprep* o, double tol);                                               // sparse.cu (K3/K4)
 void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, SymDev* out);   // symmetry.cu

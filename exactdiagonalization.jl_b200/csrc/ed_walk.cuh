@@ -33,10 +33,12 @@ template <typename F>
 __device__ __forceinline__ void walk_line(const WalkCtx& W, int64_t i, F&& emit) {
   const uint64_t b = W.words[i];
   c128 inv_self = make_c128(1.0, 0.0);
+  c128 a_self = make_c128(1.0, 0.0);
   if (W.reduced) {
-    c128 a_self = reduced_rep_amp(W.S, W.R, i);
+    a_self = reduced_rep_amp(W.S, W.R, i);
+    if (W.side == ED_SIDE_RIGHT) a_self = cconj(a_self);
     // row: one(S)/ampl_row (reduced_operator_representation.jl:66); column: one(S)/conj(ampl_col) (:98)
-    inv_self = cinv(W.side == ED_SIDE_LEFT ? a_self : cconj(a_self));
+    inv_self = cinv(a_self);
   }
   for (int t = 0; t < W.n_terms; ++t) {
     const uint64_t m = W.mask[t];
@@ -45,6 +47,8 @@ __device__ __forceinline__ void walk_line(const WalkCtx& W, int64_t i, F&& emit)
     const c128 a = load_amp(W, t);
     if (!W.reduced) {
       emit(rank_word_dyn(W.L, b2), a);
+    } else if (b2 == b) {
+      emit(i, cmul(cmul(a, a_self), inv_self));   // diagonal hit: the word is the representative itself, no orbit scan
     } else {
       if (rank_word_dyn(W.L, b2) < 0) { emit((int64_t)-1, a); continue; }  // not in the parent basis (:75-76)
       c128 a2;

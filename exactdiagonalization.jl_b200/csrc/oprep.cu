@@ -201,6 +201,11 @@ int ed_oprep_set_kernel(ed_oprep* oprep, int32_t which) {
 }
 
 static void apply_dispatch(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
+  if (o->csr[side] && o->kernel_choice != 1 && o->x_seg_ptr.empty()) {   // cached matrix: bandwidth-bound SpMV
+    if (o->rbasis) ED_REQUIRE(dtype == ED_C128, ED_ERR_ARGUMENT, "a reduced operator representation is ComplexF64: vectors must be ED_C128");
+    ed_apply_csr(o, out, x, dtype, side, accumulate, alpha_dot);
+    return;
+  }
   const bool fast = !o->rbasis && o->kernel_choice == 0 && ed_apply_u1_supported(o, dtype, side);
   ED_REQUIRE(o->x_seg_ptr.empty() || fast, ED_ERR_UNSUPPORTED,
              "segmented input vectors (ed_oprep_set_x_segments) are only consumed by the U(1) fast-path kernel");

@@ -114,13 +114,17 @@ static void exclusive_scan(const int64_t* in, int64_t* out, int64_t n, DevBuf<un
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
 }
 
-void ed_sparse_assemble(ed_oprep* o, double tol) {
-  const int64_t dim = o->dim;
+// Assemble lines [lo, hi) of the representation (columns for side = RIGHT, rows for side = LEFT): merged, chopped,
+// index-sorted entries.  ptr has hi-lo+1 entries (1-based positions like colptr), idx is 1-based.
+static void assemble_lines(ed_oprep* o, double tol, int side, int64_t lo, int64_t hi, DevBuf<int64_t>& ptr,
+                           DevBuf<int64_t>& idx, DevBuf<double>& val, int64_t& nnz_out) {
+  const int64_t nlines = hi - lo;
   const int cplx = o->is_complex ? 1 : 0;
-  WalkCtx W = ed_make_walk_ctx(o, ED_SIDE_RIGHT);  // column iterator
-  o->sp_colptr.alloc((size_t)dim + 1);
-  // columns are processed in batches so the scratch stays bounded
-  const int64_t BATCH = 1ll << 22;
+  WalkCtx W = ed_make_walk_ctx(o, side);
+  ptr.alloc((size_t)nlines + 1);
+  // lines are processed in batches so the scratch stays bounded (~2^28 raw entries)
+  int64_t BATCH = 1ll << 22;
+  if (W.n_terms > 64) BATCH = std::max<int64_t>(1 << 16, (1ll << 28) / W.n_terms);
   DevBuf<unsigned char> tmp;
   DevBuf<int64_t> counts, offs, kept, out_offs;
   DevBuf<int64_t> raw_row;
@@ -129,8 +133,8 @@ void ed_sparse_assemble(ed_oprep* o, double tol) {
   std::vector<DevBuf<double>> vals_parts;
   std::vector<int64_t> part_nnz;
   int64_t nnz_total = 0;
-  for (int64_t c0 = 0; c0 < dim; c0 += BATCH) {
-    const int64_t nc = std::min(BATCH, dim - c0);
+  for (int64_t c0 = 0; c0 < nlines; c0 += BATCH) {
+    const int64_t nc = std::min(BATCH, nlines - c0);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 127) / 128, (int64_t)ed_sm_count() * 16));
     counts.alloc((size_t)nc + 1);
     offs.alloc((size_t)nc + 1);
@@ -138,14 +142,14 @@ void ed_sparse_assemble(ed_oprep* o, double tol) {
     out_offs.alloc((size_t)nc + 1);
     ED_CUDA(cudaMemsetAsync(counts.p, 0, (size_t)(nc + 1) * sizeof(int64_t), ed_stream()));
     ED_CUDA(cudaMemsetAsync(kept.p, 0, (size_t)(nc + 1) * sizeof(int64_t), ed_stream()));
-    ED_LAUNCH(k3_count_matches, grid, 128, 0, W, c0, nc, counts.p);
+    ED_LAUNCH(k3_count_matches, grid, 128, 0, W, lo + c0, nc, counts.p);
     exclusive_scan(counts.p, offs.p, nc + 1, tmp);
     int64_t raw_total = 0;
     ED_CUDA(cudaMemcpyAsync(&raw_total, offs.p + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));
     ED_CUDA(cudaStreamSynchronize(ed_stream()));
     raw_row.alloc((size_t)std::max<int64_t>(raw_total, 1));
     raw_val.alloc((size_t)std::max<int64_t>(raw_total, 1));
-    ED_LAUNCH(k4_fill_raw, grid, 128, 0, W, c0, nc, offs.p, raw_row.p, raw_val.p);
+    ED_LAUNCH(k4_fill_raw, grid, 128, 0, W, lo + c0, nc, offs.p, raw_row.p, raw_val.p);
     ED_LAUNCH(k4_merge_chop, grid, 128, 0, nc, offs.p, raw_row.p, raw_val.p, tol, cplx, kept.p);
     exclusive_scan(kept.p, out_offs.p, nc + 1, tmp);
     int64_t nnz_b = 0;
@@ -155,27 +159,178 @@ void ed_sparse_assemble(ed_oprep* o, double tol) {
     vals_parts.emplace_back((size_t)std::max<int64_t>(nnz_b, 1) * (cplx ? 2 : 1));
     ED_LAUNCH(k4_gather, grid, 128, 0, nc, offs.p, raw_row.p, raw_val.p, out_offs.p, (int64_t)0, rows_parts.back().p,
               vals_parts.back().p, cplx);
-    ED_LAUNCH(k_colptr, grid, 128, 0, c0 + nc == dim ? nc : nc - 1, out_offs.p, nnz_total, o->sp_colptr.p + c0);
+    ED_LAUNCH(k_colptr, grid, 128, 0, nc, out_offs.p, nnz_total, ptr.p + c0);
     part_nnz.push_back(nnz_b);
     nnz_total += nnz_b;
     ED_CUDA(cudaStreamSynchronize(ed_stream()));
   }
-  if (dim == 0) {
+  if (nlines == 0) {
     int64_t one = 1;
-    o->sp_colptr.upload(&one, 1);
+    ptr.upload(&one, 1);
   }
-  o->sp_rowval.alloc((size_t)std::max<int64_t>(nnz_total, 1));
-  o->sp_nzval.alloc((size_t)std::max<int64_t>(nnz_total, 1) * (cplx ? 2 : 1));
+  raw_row.release();
+  raw_val.release();
+  idx.alloc((size_t)std::max<int64_t>(nnz_total, 1));
+  val.alloc((size_t)std::max<int64_t>(nnz_total, 1) * (cplx ? 2 : 1));
   int64_t at = 0;
   for (size_t p = 0; p < part_nnz.size(); ++p) {
     if (part_nnz[p]) {
-      ED_CUDA(cudaMemcpyAsync(o->sp_rowval.p + at, rows_parts[p].p, (size_t)part_nnz[p] * sizeof(int64_t), cudaMemcpyDeviceToDevice, ed_stream()));
-      ED_CUDA(cudaMemcpyAsync(o->sp_nzval.p + at * (cplx ? 2 : 1), vals_parts[p].p, (size_t)part_nnz[p] * (cplx ? 16 : 8), cudaMemcpyDeviceToDevice, ed_stream()));
+      ED_CUDA(cudaMemcpyAsync(idx.p + at, rows_parts[p].p, (size_t)part_nnz[p] * sizeof(int64_t), cudaMemcpyDeviceToDevice, ed_stream()));
+      ED_CUDA(cudaMemcpyAsync(val.p + at * (cplx ? 2 : 1), vals_parts[p].p, (size_t)part_nnz[p] * (cplx ? 16 : 8), cudaMemcpyDeviceToDevice, ed_stream()));
     }
     at += part_nnz[p];
+    ED_CUDA(cudaStreamSynchronize(ed_stream()));
+    rows_parts[p].release();
+    vals_parts[p].release();
   }
   ED_CUDA(cudaStreamSynchronize(ed_stream()));
-  o->sp_nnz = nnz_total;
+  nnz_out = nnz_total;
+}
+
+void ed_sparse_assemble(ed_oprep* o, double tol) {
+  assemble_lines(o, tol, ED_SIDE_RIGHT, 0, o->dim, o->sp_colptr, o->sp_rowval, o->sp_nzval, o->sp_nnz);  // column iterator
+}
+
+// ------------------------------------------------------------------ cached CSR + SpMV
+// The assembled rows [row_lo, row_hi) of the representation kept on device in a compact form (0-based int32 columns,
+// real values when every imaginary part is exactly zero); repeated matvecs then run as a bandwidth-bound SpMV
+// instead of redoing the term walk / orbit searches.  Entries are NOT chopped (tol = 0), so the cached apply agrees
+// with the matrix-free one to rounding.
+__global__ void __launch_bounds__(256)
+k_csr_compact(int64_t n_lines, int64_t nnz, const int64_t* __restrict__ ptr1, const int64_t* __restrict__ idx1,
+              const double* __restrict__ val, int val_complex, int64_t* __restrict__ rowptr0, int32_t* __restrict__ col0,
+              int* __restrict__ any_imag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int flag = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += stride) {
+    col0[i] = (int32_t)(idx1[i] - 1);
+    if (val_complex && val[2 * i + 1] != 0.0) flag = 1;
+  }
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= n_lines; i += stride) rowptr0[i] = ptr1[i] - 1;
+  if (flag) atomicExch(any_imag, 1);
+}
+
+__global__ void __launch_bounds__(256) k_take_real(int64_t nnz, const double* __restrict__ cval, double* __restrict__ rval) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) rval[i] = cval[2 * i];
+}
+
+__device__ __forceinline__ c128 ld_mat(const c128* v, int64_t i) { return ldg_c128(v + i); }
+__device__ __forceinline__ double ld_mat(const double* v, int64_t i) { return __ldg(v + i); }
+__device__ __forceinline__ void mat_fma(double& acc, double a, double x) { acc = fma(a, x, acc); }
+__device__ __forceinline__ void mat_fma(c128& acc, double a, c128 x) { acc.re = fma(a, x.re, acc.re); acc.im = fma(a, x.im, acc.im); }
+__device__ __forceinline__ void mat_fma(c128& acc, c128 a, c128 x) { fma_acc(acc, a, x); }
+
+// one warp per row: lanes stride the row's entries, shuffle reduction (fixed tree -> deterministic)
+template <typename VecT, typename ValT>
+__global__ void __launch_bounds__(256)
+k_spmv_csr(int64_t n_rows, int64_t row_lo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+           const ValT* __restrict__ val, const VecT* __restrict__ x, VecT* __restrict__ y, int accumulate,
+           double* __restrict__ dot_partials) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double dre = 0.0, dim_ = 0.0;
+  for (int64_t r = warp0; r < n_rows; r += nwarps) {
+    const int64_t b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
+    VecT acc = vzero((VecT*)nullptr);
+    for (int64_t p = b + lane; p < e; p += 32) mat_fma(acc, ld_mat(val, p), ldg_val(x + __ldg(col + p)));
+    if (sizeof(VecT) == 16) {
+      c128* a = reinterpret_cast<c128*>(&acc);
+      a->re = warp_sum(a->re);
+      a->im = warp_sum(a->im);
+    } else {
+      double* a = reinterpret_cast<double*>(&acc);
+      *a = warp_sum(*a);
+    }
+    if (lane == 0) {
+      if (accumulate) acc = (sizeof(VecT) == 16) ? acc : acc;
+      VecT out = acc;
+      if (accumulate) {
+        VecT old = y[r];
+        fma_acc(out, 1.0, old);
+      }
+      st_val(y + r, out);
+      if (dot_partials) dot_acc(dre, dim_, ldg_val(x + row_lo + r), out);
+    }
+  }
+  if (dot_partials) {
+    __shared__ double s_red[2][8];
+    dre = warp_sum(dre);
+    dim_ = warp_sum(dim_);
+    if (lane == 0) { s_red[0][threadIdx.x >> 5] = dre; s_red[1][threadIdx.x >> 5] = dim_; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, c = 0;
+      for (int w = 0; w < 8; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
+      dot_partials[2 * blockIdx.x] = a;
+      dot_partials[2 * blockIdx.x + 1] = c;
+    }
+  }
+}
+
+void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
+
+void ed_csr_cache_build(ed_oprep* o, int side) {
+  auto cache = std::make_shared<CsrCache>();
+  cache->side = side;
+  cache->row_lo = o->row_lo;
+  cache->row_hi = o->row_hi;
+  const int64_t n = o->row_hi - o->row_lo;
+  ED_REQUIRE(o->dim < (1ll << 31), ED_ERR_UNSUPPORTED, "cached CSR needs dimension < 2^31");
+  DevBuf<int64_t> ptr1, idx1;
+  DevBuf<double> val;
+  int64_t nnz = 0;
+  assemble_lines(o, 0.0, side, o->row_lo, o->row_hi, ptr1, idx1, val, nnz);
+  cache->nnz = nnz;
+  cache->rowptr.alloc((size_t)n + 1);
+  cache->col.alloc((size_t)std::max<int64_t>(nnz, 1));
+  DevBuf<int> flag(1);
+  ED_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), ed_stream()));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((std::max(nnz, n + 1) + 255) / 256, (int64_t)ed_sm_count() * 16));
+  ED_LAUNCH(k_csr_compact, grid, 256, 0, n, nnz, ptr1.p, idx1.p, val.p, o->is_complex ? 1 : 0, cache->rowptr.p, cache->col.p, flag.p);
+  int any_imag = 0;
+  flag.download(&any_imag, 1);
+  idx1.release();
+  ptr1.release();
+  if (o->is_complex && !any_imag) {
+    cache->val_complex = false;
+    cache->val.alloc((size_t)std::max<int64_t>(nnz, 1));
+    ED_LAUNCH(k_take_real, grid, 256, 0, nnz, val.p, cache->val.p);
+    ED_CUDA(cudaStreamSynchronize(ed_stream()));
+  } else {
+    cache->val_complex = o->is_complex;
+    cache->val = std::move(val);
+  }
+  o->csr[side] = cache;
+}
+
+void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
+  CsrCache* c = o->csr[side].get();
+  ED_REQUIRE(c && c->row_lo == o->row_lo && c->row_hi == o->row_hi, ED_ERR_ARGUMENT,
+             "the cached matrix was built for a different row range; rebuild it after ed_oprep_set_rows");
+  const int64_t n = c->row_hi - c->row_lo;
+  if (n <= 0) {
+    if (alpha_dot) ED_CUDA(cudaMemsetAsync(alpha_dot, 0, 2 * sizeof(double), ed_stream()));
+    return;
+  }
+  ED_REQUIRE(!(c->val_complex && dtype == ED_F64), ED_ERR_ARGUMENT, "a complex operator representation needs ComplexF64 vectors");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ed_sm_count() * 16));
+  static thread_local DevBuf<double> pbuf;
+  double* partials = nullptr;
+  if (alpha_dot) {
+    if (pbuf.n < (size_t)2 * grid) pbuf.alloc((size_t)2 * grid);
+    partials = pbuf.p;
+  }
+  if (dtype == ED_F64)
+    ED_LAUNCH((k_spmv_csr<double, double>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->val.p,
+              reinterpret_cast<const double*>(x), reinterpret_cast<double*>(out), accumulate, partials);
+  else if (!c->val_complex)
+    ED_LAUNCH((k_spmv_csr<c128, double>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->val.p,
+              reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate, partials);
+  else
+    ED_LAUNCH((k_spmv_csr<c128, c128>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, reinterpret_cast<const c128*>(c->val.p),
+              reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate, partials);
+  if (alpha_dot) ed_reduce_pairs(partials, grid, alpha_dot);
 }
 
 extern "C" {
@@ -187,6 +342,24 @@ int ed_sparse_count(ed_oprep* oprep, double tol, int64_t* nnz_out) {
   ed_require_device();
   ed_sparse_assemble(oprep, tol);
   *nnz_out = oprep->sp_nnz;
+  ED_CATCH
+}
+
+int ed_oprep_cache_matrix(ed_oprep* oprep, int32_t side, int64_t* nnz_out) {
+  ED_TRY
+  ED_REQUIRE(oprep, ED_ERR_ARGUMENT, "null argument");
+  ED_REQUIRE(side == ED_SIDE_LEFT || side == ED_SIDE_RIGHT, ED_ERR_ARGUMENT, "bad side");
+  ed_require_device();
+  ed_csr_cache_build(oprep, side);
+  if (nnz_out) *nnz_out = oprep->csr[side]->nnz;
+  ED_CATCH
+}
+
+int ed_oprep_drop_cache(ed_oprep* oprep) {
+  ED_TRY
+  ED_REQUIRE(oprep, ED_ERR_ARGUMENT, "null argument");
+  oprep->csr[0].reset();
+  oprep->csr[1].reset();
   ED_CATCH
 }
 

@@ -104,6 +104,8 @@ SIGNATURES = {
     "ed_oprep_get_element": (C.c_int, [vp, i64, i64, vp]),
     "ed_sparse_count": (C.c_int, [vp, dbl, P(i64)]),
     "ed_sparse_fetch": (C.c_int, [vp, vp, vp, vp]),
+    "ed_oprep_cache_matrix": (C.c_int, [vp, i32, P(i64)]),
+    "ed_oprep_drop_cache": (C.c_int, [vp]),
     "ed_dense": (C.c_int, [vp, vp]),
     "ed_lanczos": (C.c_int, [vp, i32, vp, i32, u64, vp, vp, vp, i32, P(i32)]),
     "ed_lanczos_update_async": (C.c_int, [vp, vp, vp, i64, i32, vp, vp, vp, vp]),

@@ -225,6 +225,17 @@ class _AbstractOperatorRepresentation:
         self._rows = (lo, hi)
         return self
 
+    def cache_matrix(self, side: int = ED_SIDE_LEFT) -> int:
+        """Assemble the owned rows once and keep them on device: later apply!/mul!/Lanczos calls become an SpMV.
+        Returns the number of stored entries."""
+        nnz = C.c_int64()
+        check(lib.ed_oprep_cache_matrix(self._handle, side, C.byref(nnz)))
+        return nnz.value
+
+    def drop_cache(self):
+        check(lib.ed_oprep_drop_cache(self._handle))
+        return self
+
     def set_kernel(self, which: int):
         check(lib.ed_oprep_set_kernel(self._handle, which))
         return self

@@ -222,6 +222,13 @@ int ed_oprep_get_element(ed_oprep* oprep, int64_t i, int64_t j, double* value_ou
  * device copy.  tol < 0 selects the reference default sqrt(eps(Float64)). */
 int ed_sparse_count(ed_oprep* oprep, double tol, int64_t* nnz_out);
 int ed_sparse_fetch(ed_oprep* oprep, int64_t* colptr, int64_t* rowval, void* nzval);
+/* Keep the assembled rows of the representation on device (owned row range, side LEFT = rows of H, RIGHT = rows of
+ * H^T; nothing chopped) so that later ed_apply / ed_apply_async / ed_lanczos calls run as a bandwidth-bound SpMV
+ * instead of redoing the term walk -- the practical path for symmetry-reduced representations, whose matrix-free
+ * apply is instruction-bound (|G| images per hit).  ed_oprep_set_kernel(oprep, 1) bypasses the cache; rebuild after
+ * ed_oprep_set_rows.  The reference's get_row/get_column/Matrix users are served by the iterators above. */
+int ed_oprep_cache_matrix(ed_oprep* oprep, int32_t side, int64_t* nnz_out);
+int ed_oprep_drop_cache(ed_oprep* oprep);
 /* Matrix(opr) (:121-132): dense column-major dim x dim, no chop.  out is a host buffer of the
  * representation's dtype. */
 int ed_dense(ed_oprep* oprep, void* out);

@@ -189,6 +189,7 @@ class _AbstractOperatorRepresentation:
 
     _handle = None
     operator: Operator
+    __array_ufunc__ = None   # numpy defers to __rmul__: `state * opr` works like the reference's Base.:(*)(state, opr)
 
     # -- traits
     @property

@@ -210,6 +210,8 @@ struct SymDev {
   int n_chunks = 0;        // ceil(bits / 8)
   uint64_t fullmask = 0;
   DevBuf<uint64_t> lut;    // [(g*n_chunks + c)*256 + byte] -> image bits (flip already folded in chunk 0.. see symmetry.cu)
+  int n_chunks6 = 0;       // ceil(bits / 6)
+  DevBuf<uint64_t> lut6;   // [(g*n_chunks6 + c)*64 + v]: the same action in 6-bit chunks (shared-memory streaming, reduced_staged.cu)
   DevBuf<double> chi;      // [n_ops][2]
   DevBuf<int32_t> inverse; // [n_ops]
   DevBuf<uint8_t> chi_is_one;  // [n_ops]  |chi-1| <= tol
@@ -295,7 +297,9 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
                  double* alpha_dot);
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
-                      double* alpha_dot);                                                       // reduced.cu (K6)
+                      double* alpha_dot);
+bool ed_apply_reduced_staged_supported(ed_oprep* o);                                            // reduced_staged.cu
+void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);                                                       // reduced.cu (K6)
 void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot);
 void ed_sparse_assemble(ed_oprep* o, double tol);                                               // sparse.cu (K3/K4)
 void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, SymDev* out);   // symmetry.cu

@@ -9,6 +9,7 @@
 // registers, character of the minimising element, orbit size of the representative (see
 // reduced_map_word in ed_device.cuh).  Diagonal hits (b' == b) skip the search.
 #include <algorithm>
+#include <cstdlib>
 
 #include "ed_device.cuh"
 
@@ -79,6 +80,12 @@ k6_apply_reduced(LookupDesc L, SymDesc S, RLookupDesc R, int64_t row_lo, int64_t
 }
 
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot) {
+  // large row ranges: word-parallel orbit sweep (reduced_staged.cu); small ones: the simple row-per-thread kernel below
+  static const bool force_simple = getenv("EDCUDA_K6_SIMPLE") != nullptr;
+  if (!force_simple && ed_apply_reduced_staged_supported(o)) {
+    ed_apply_reduced_staged(o, out, x, side, accumulate, alpha_dot);
+    return;
+  }
   ed_upload_terms(o);
   ed_rbasis* rb = o->rbasis;
   ed_basis* parent = rb->parent;

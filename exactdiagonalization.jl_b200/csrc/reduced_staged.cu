@@ -1,0 +1,254 @@
+// K6 (staged): matrix-free apply for a ReducedOperatorRepresentation, reorganised for the GPU.
+//
+// Same arithmetic as k6_apply_reduced in reduced.cu (reference: Symmetry/reduced_operator_representation.jl:57-116,
+// Symmetry/symmetry_reduce_generic.jl:51-101), but the expensive part -- reducing every off-diagonal column word to
+// its orbit minimum over the |G| group elements -- is pulled out of the per-row loop and run WORD-parallel:
+//   A  k6a_count / k6a_emit  : per row, the off-diagonal column words of the term walk, compacted in (row, term) order
+//   B  k6b_canonicalize      : every thread holds 4 words in registers and sweeps the group; the 6-bit-chunk
+//                              permutation LUT of each element is streamed through shared memory once per CTA pass
+//                              (1024 words), so the sweep is pure LDS + ALU with no divergence
+//   C  k6c_combine           : per row, term walk again in the reference's order; each hit reads its (minimum word,
+//                              element) pair, finds the representative (bucketed search), forms
+//                              a * conj(chi_g)/sqrt(N_col) / amp_row and accumulates -- row-owner, deterministic
+// Rows are processed in batches so the scratch (10 bytes per hit) stays bounded.
+#include <algorithm>
+#include <cstdlib>
+#include <cub/cub.cuh>
+
+#include "ed_device.cuh"
+
+void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
+
+struct K6Terms {
+  int n_terms;
+  const uint64_t* mask;
+  const uint64_t* match;
+  const uint64_t* target;
+  const double* amp;
+  int amp_complex;
+};
+
+__global__ void __launch_bounds__(256)
+k6a_count(K6Terms T, const uint64_t* __restrict__ rwords, int64_t row0, int64_t n, int64_t* __restrict__ counts) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = __ldg(rwords + row0 + i);
+    int c = 0;
+    for (int t = 0; t < T.n_terms; ++t) {
+      const uint64_t m = __ldg(T.mask + t);
+      if ((b & m) == __ldg(T.match + t) && ((b & ~m) | __ldg(T.target + t)) != b) ++c;
+    }
+    counts[i] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k6a_emit(K6Terms T, const uint64_t* __restrict__ rwords, int64_t row0, int64_t n, const int64_t* __restrict__ offs,
+         uint64_t* __restrict__ hit_words) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = __ldg(rwords + row0 + i);
+    int64_t at = offs[i];
+    for (int t = 0; t < T.n_terms; ++t) {
+      const uint64_t m = __ldg(T.mask + t);
+      if ((b & m) != __ldg(T.match + t)) continue;
+      const uint64_t b2 = (b & ~m) | __ldg(T.target + t);
+      if (b2 != b) hit_words[at++] = b2;
+    }
+  }
+}
+
+// B: words[i] <- min_g g(words[i]); garg[i] <- the index i* with words[i] = g_{i*}(min) that the reference's Dict keeps
+// (largest such index, see reduced_map_word).  lut6 layout: [g][chunk][64] uint64.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k6b_canonicalize(int n_ops, const uint64_t* __restrict__ lut6, const int32_t* __restrict__ inverse, int64_t n_words,
+                 uint64_t* __restrict__ words, uint16_t* __restrict__ garg) {
+  constexpr int W = 4;          // words per thread
+  constexpr int GB = 4;         // group elements staged per barrier (2 x GB x NCH x 512 B of shared memory)
+  __shared__ __align__(16) uint64_t s_lut[2][GB * NCH * 64];
+  __shared__ int s_inv[2][GB];
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * (256 * W);
+  uint64_t w[W], best[W];
+  int besti[W];
+  uint32_t off[W][NCH];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int64_t i = base + tid + k * 256;
+    w[k] = i < n_words ? words[i] : 0ull;
+    best[k] = w[k];
+    besti[k] = 0;   // identity (element 0, its own inverse)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) off[k][c] = (uint32_t)((w[k] >> (6 * c)) & 63ull) + c * 64;
+  }
+  const int n_batches = (n_ops + GB - 1) / GB;
+  auto stage = [&](int batch, int buf) {
+    const int g0 = batch * GB;
+    const int ng = min(GB, n_ops - g0);
+    const uint64_t* src = lut6 + (size_t)g0 * NCH * 64;
+    for (int i = tid; i < ng * NCH * 64; i += 256) s_lut[buf][i] = __ldg(src + i);
+    if (tid < ng) s_inv[buf][tid] = __ldg(inverse + g0 + tid);
+  };
+  stage(0, 0);
+  __syncthreads();
+  for (int batch = 0; batch < n_batches; ++batch) {
+    const int buf = batch & 1;
+    if (batch + 1 < n_batches) stage(batch + 1, buf ^ 1);
+    const int g0 = batch * GB;
+    const int ng = min(GB, n_ops - g0);
+    for (int gi = (batch == 0 ? 1 : 0); gi < ng; ++gi) {   // element 0 is the identity
+      const uint64_t* L = s_lut[buf] + gi * NCH * 64;
+      const int inv = s_inv[buf][gi];
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        uint64_t im = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) im |= L[off[k][c]];
+        if (im < best[k]) { best[k] = im; besti[k] = inv; }
+        else if (im == best[k] && inv > besti[k]) besti[k] = inv;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int64_t i = base + tid + k * 256;
+    if (i < n_words) { words[i] = best[k]; garg[i] = (uint16_t)besti[k]; }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int64_t n, int64_t out_row0,
+            const int64_t* __restrict__ offs, const uint64_t* __restrict__ min_words, const uint16_t* __restrict__ garg,
+            int conj_side, const c128* __restrict__ x, c128* __restrict__ out, int accumulate,
+            double* __restrict__ dot_partials, int partial_slot0) {
+  double dre = 0.0, dim_ = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row0 + i;
+    const uint64_t b = __ldg(R.words + r);
+    c128 a_self = reduced_rep_amp(S, R, r);
+    if (conj_side) a_self = cconj(a_self);
+    const c128 inv_self = cinv(a_self);
+    c128 acc = accumulate ? out[out_row0 + i] : make_c128(0.0, 0.0);
+    int64_t at = offs[i];
+    for (int t = 0; t < T.n_terms; ++t) {
+      const uint64_t m = __ldg(T.mask + t);
+      if ((b & m) != __ldg(T.match + t)) continue;
+      const uint64_t b2 = (b & ~m) | __ldg(T.target + t);
+      const c128 a = T.amp_complex ? make_c128(__ldg(T.amp + 2 * t), __ldg(T.amp + 2 * t + 1)) : make_c128(__ldg(T.amp + t), 0.0);
+      int64_t j;
+      c128 a2;
+      if (b2 == b) {
+        j = r;
+        a2 = a_self;
+      } else {
+        const uint64_t mw = min_words[at];
+        const int gi = garg[at];
+        ++at;
+        if (rank_word_dyn(L, b2) < 0) continue;                 // not in the parent basis
+        j = rank_reduced(R, mw);
+        if (j < 0) continue;                                     // orbit not in this irrep
+        const double inv_norm = 1.0 / sqrt((double)__ldg(R.orbit_size + j));
+        a2 = make_c128(__ldg(S.chi + 2 * gi) * inv_norm, -__ldg(S.chi + 2 * gi + 1) * inv_norm);
+        if (conj_side) a2 = cconj(a2);
+      }
+      fma_acc(acc, cmul(cmul(a, a2), inv_self), ldg_c128(x + j));
+    }
+    st_val(out + out_row0 + i, acc);
+    if (dot_partials) dot_acc(dre, dim_, ldg_c128(x + r), acc);
+  }
+  if (dot_partials) {
+    __shared__ double s_red[2][4];
+    dre = warp_sum(dre);
+    dim_ = warp_sum(dim_);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][wid] = dre; s_red[1][wid] = dim_; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0, c = 0;
+      for (int w = 0; w < (blockDim.x >> 5); ++w) { a += s_red[0][w]; c += s_red[1][w]; }
+      dot_partials[2 * (partial_slot0 + blockIdx.x)] = a;
+      dot_partials[2 * (partial_slot0 + blockIdx.x) + 1] = c;
+    }
+  }
+}
+
+struct K6Scratch {
+  DevBuf<int64_t> counts, offs;
+  DevBuf<uint64_t> words;
+  DevBuf<uint16_t> garg;
+  DevBuf<unsigned char> tmp;
+  DevBuf<double> partials;
+};
+
+static K6Scratch& scratch() {
+  static thread_local K6Scratch s;
+  return s;
+}
+
+bool ed_apply_reduced_staged_supported(ed_oprep* o) {
+  const ed_rbasis* rb = o->rbasis;
+  const char* e = getenv("EDCUDA_K6_MIN_ROWS");   // rows below which the simple row-per-thread kernel is used
+  const int64_t min_rows = e ? atoll(e) : 2048;
+  return rb && rb->symdev.lut6.n > 0 && rb->symdev.n_chunks6 <= 11 && (o->row_hi - o->row_lo) >= min_rows;
+}
+
+void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot) {
+  ed_upload_terms(o);
+  ed_rbasis* rb = o->rbasis;
+  ed_basis* parent = rb->parent;
+  if (parent->kind == ED_BASIS_LIST) parent->materialize();
+  const TermsDev& TD = side == ED_SIDE_LEFT ? o->terms_left : o->terms_right;
+  K6Terms T{TD.n_terms, TD.mask.p, TD.match.p, TD.target.p, TD.amp.p, TD.is_complex ? 1 : 0};
+  const int64_t n_rows = o->row_hi - o->row_lo;
+  RLookupDesc R;
+  R.words = rb->words.p; R.orbit_size = rb->orbit_size.p; R.last_stab = rb->last_stab.p;
+  R.bucket_start = rb->bucket_start.p; R.bucket_shift = rb->bucket_shift; R.n_buckets = rb->n_buckets; R.dim = rb->dim;
+  const SymDesc S = rb->symdesc();
+  const LookupDesc L = parent->desc();
+  K6Scratch& sc = scratch();
+  // batch rows so that a batch emits at most ~2^27 hits (upper bound: every term fires)
+  const int64_t cap_hits = 1ll << 27;
+  const int64_t batch_rows = std::max<int64_t>(4096, cap_hits / std::max(1, T.n_terms / 2));
+  const int n_batches = (int)((n_rows + batch_rows - 1) / batch_rows);
+  const int sm = ed_sm_count();
+  const int grid_c_max = sm * 16;
+  if (alpha_dot && sc.partials.n < (size_t)2 * grid_c_max * n_batches) sc.partials.alloc((size_t)2 * grid_c_max * n_batches);
+  int slots_used = 0;
+  for (int64_t b0 = 0; b0 < n_rows; b0 += batch_rows) {
+    const int64_t nb = std::min(batch_rows, n_rows - b0);
+    const int64_t row0 = o->row_lo + b0;
+    if (sc.counts.n < (size_t)nb + 1) { sc.counts.alloc((size_t)nb + 1); sc.offs.alloc((size_t)nb + 1); }
+    ED_CUDA(cudaMemsetAsync(sc.counts.p + nb, 0, sizeof(int64_t), ed_stream()));
+    const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 255) / 256, (int64_t)sm * 16));
+    ED_LAUNCH(k6a_count, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.counts.p);
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
+    if (sc.tmp.n < bytes) sc.tmp.alloc(bytes);
+    cub::DeviceScan::ExclusiveSum(sc.tmp.p, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    int64_t n_hits = 0;
+    ED_CUDA(cudaMemcpyAsync(&n_hits, sc.offs.p + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));
+    ED_CUDA(cudaStreamSynchronize(ed_stream()));
+    if (sc.words.n < (size_t)std::max<int64_t>(n_hits, 1)) {
+      sc.words.alloc((size_t)std::max<int64_t>(n_hits, 1));
+      sc.garg.alloc((size_t)std::max<int64_t>(n_hits, 1));
+    }
+    if (n_hits > 0) {
+      ED_LAUNCH(k6a_emit, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.offs.p, sc.words.p);
+      const int grid_b = (int)((n_hits + 1023) / 1024);
+      const int nch = rb->symdev.n_chunks6;
+      const uint64_t* lut6 = rb->symdev.lut6.p;
+      const int32_t* inv = rb->symdev.inverse.p;
+      if (nch <= 4) ED_LAUNCH(k6b_canonicalize<4>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+      else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+      else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+      else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+    }
+    const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 127) / 128, (int64_t)grid_c_max));
+    ED_LAUNCH(k6c_combine, grid_c, 128, 0, T, L, S, R, row0, nb, b0, sc.offs.p, sc.words.p, sc.garg.p,
+              side == ED_SIDE_RIGHT ? 1 : 0, reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate,
+              alpha_dot ? sc.partials.p : nullptr, slots_used);
+    slots_used += grid_c;
+  }
+  if (alpha_dot) ed_reduce_pairs(sc.partials.p, slots_used, alpha_dot);
+}

@@ -77,6 +77,31 @@ void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, 
       }
     }
   }
+  // the same action in 6-bit chunks for the word-parallel orbit sweep (k6b_canonicalize)
+  int n_chunks6 = std::max(1, (space.bits + 5) / 6);
+  // padded to the kernel's compile-time chunk counts (4, 6, 8, 11); padding chunks only ever see the value 0 -> image 0
+  n_chunks6 = n_chunks6 <= 4 ? 4 : n_chunks6 <= 6 ? 6 : n_chunks6 <= 8 ? 8 : 11;
+  std::vector<uint64_t> lut6((size_t)G * n_chunks6 * 64, 0);
+  for (int g = 0; g < G; ++g) {
+    for (int i = 0; i < n; ++i) {
+      int j = sym.perm[(size_t)g * n + i];
+      for (int k = 0; k < space.width[i]; ++k) tgt[space.offset[i] + k] = space.offset[j] + k;
+    }
+    for (int c = 0; c < n_chunks6; ++c) {
+      uint64_t all = 0;
+      for (int q = 0; q < 6; ++q)
+        if (6 * c + q < space.bits) all |= 1ull << tgt[6 * c + q];
+      for (int v = 0; v < 64; ++v) {
+        uint64_t im = 0;
+        for (int q = 0; q < 6; ++q)
+          if ((v >> q & 1) && 6 * c + q < space.bits) im |= 1ull << tgt[6 * c + q];
+        if (sym.flip[g]) im ^= all;
+        lut6[((size_t)g * n_chunks6 + c) * 64 + v] = im;
+      }
+    }
+  }
+  out->n_chunks6 = n_chunks6;
+  out->lut6.upload(lut6);
   out->n_ops = G;
   out->n_chunks = n_chunks;
   out->fullmask = space.fullmask();

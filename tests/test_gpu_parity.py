@@ -541,8 +541,15 @@ def test_reduced_operator_chain4_golden(gpu_ed, golden):
             ropr.get_element(*bad)
 
 
+@pytest.fixture(params=["simple", "staged"])
+def k6_path(request, monkeypatch):
+    """Run the reduced-representation tests through both K6 implementations (row-per-thread / word-parallel staged)."""
+    monkeypatch.setenv("EDCUDA_K6_MIN_ROWS", "1" if request.param == "staged" else "1000000000000")
+    return request.param
+
+
 @pytest.mark.parametrize("n,qn", [(7, 1), (8, 0), (10, 0)])
-def test_reduced_apply_vs_oracle(gpu_ed, n, qn):
+def test_reduced_apply_vs_oracle(gpu_ed, n, qn, k6_path):
     ed = gpu_ed
     L = ed.lattices
     hs, h = ed.models.j1j2_chain(n, 0.5)
@@ -594,7 +601,7 @@ def test_reduced_apply_vs_oracle(gpu_ed, n, qn):
         assert np.allclose(sorted(spectrum), full, atol=1e-9)     # spectra union (test_reduced_representation.jl:236-252)
 
 
-def test_reduced_square_4x4_momentum_sectors(gpu_ed, golden):
+def test_reduced_square_4x4_momentum_sectors(gpu_ed, golden, k6_path):
     """Config 2: 4x4 square Heisenberg, all 16 momentum sectors: CSC structure bit-exact vs the oracle on two
     sectors (the oracle's Python loops are slow), ground state over all sectors = known answer."""
     ed = gpu_ed
@@ -625,7 +632,7 @@ def test_reduced_square_4x4_momentum_sectors(gpu_ed, golden):
     assert abs(e_min[0] - golden["known_answers"]["sq4x4_E0"]) < 1e-9       # ground state sits at k = 0
 
 
-def test_triangular_space_group_small(gpu_ed):
+def test_triangular_space_group_small(gpu_ed, k6_path):
     """3x3... the 6x6 configuration's machinery (T x| C6v, k=0 A1, 432-element groups) on a 4x4 torus where the
     oracle can follow: representatives, mapping and reduced matvec agree; Burnside count checks the dimension."""
     ed = gpu_ed

@@ -99,52 +99,63 @@ def build_model(ed, w):
     return hs, h, n_bonds
 
 
+class CpuReference:
+    """Reference-algorithm restatement (oracle C twin: term walk in order + binary search per hit + static row
+    partition = the reference's apply_parallel!) on a bounded contiguous row sample, all host threads."""
+
+    def __init__(self, w, threads=None):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import numpy as np
+        import ed_oracle_c as OC
+        sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
+        import edcuda as ed   # only for the model's term list (host code); no engine compute on this path
+        self.np, self.OC = np, OC
+        if threads:
+            OC.set_num_threads(threads)
+        self.n = w["n"]
+        _, h, self.n_bonds = build_model(ed, w)
+        self.terms = h.arrays()
+        self.basis = OC.basis_fixed_popcount(self.n, self.n // 2)
+        self.dim = len(self.basis)
+        self.x = np.random.default_rng(20260717 + 5).standard_normal(self.dim)
+        # calibrate on a small slice in the middle of the basis
+        self.n0 = min(self.dim, 20000 * OC.num_threads())
+        self.rate = self.n0 / self._time(self.n0)          # rows per second
+
+    def _time(self, rows):
+        lo = max(0, self.dim // 2 - rows // 2)
+        out = self.np.zeros(rows)
+        t0 = time.perf_counter()
+        self.OC.apply(self.basis, self.terms, self.x, out, lo, lo + rows)
+        self._last = (lo, rows)
+        return time.perf_counter() - t0
+
+    def sample(self, target_seconds):
+        OC = self.OC
+        rows = int(min(self.dim, max(self.n0, self.rate * target_seconds)))
+        dt = self._time(rows)
+        lo, rows = self._last
+        matvec_s = dt * self.dim / rows
+        return {"value": 1.0 / matvec_s, "unit": "matvec/s", "cores": OC.num_threads(), "kind": "port",
+                "sample": f"rows [{lo},{lo + rows}) of {self.dim} ({rows / self.dim:.4%}) timed {dt:.2f}s on {OC.num_threads()} OpenMP threads, "
+                          f"extrapolated to the full matvec; reference-algorithm restatement (oracle/ed_oracle_c.c), not Julia",
+                "seconds_per_matvec_extrapolated": matvec_s, "gnnz_per_s": nnz_eff(self.n, self.n_bonds) / matvec_s / 1e9}
+
+
 def cpu_baseline(w, target_seconds=12.0, threads=None):
-    """Reference-algorithm restatement (oracle C twin) on a bounded contiguous row sample, all host threads."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
-    import ed_oracle_c as OC
-    sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
-    import edcuda as ed   # only for the model's term list (host code); no engine compute on this path
-    if threads:
-        OC.set_num_threads(threads)
-    n = w["n"]
-    _, h, n_bonds = build_model(ed, w)
-    terms = h.arrays()
-    basis = OC.basis_fixed_popcount(n, n // 2)
-    dim = len(basis)
-    rng = np.random.default_rng(20260717 + 5)
-    x = rng.standard_normal(dim)
-    # calibrate on a small slice in the middle of the basis, then size the sample for ~target_seconds
-    mid = dim // 2
-    n0 = min(dim, 20000 * OC.num_threads())
-    lo0 = max(0, mid - n0 // 2)
-    out = np.zeros(n0)
-    t0 = time.perf_counter()
-    OC.apply(basis, terms, x, out, lo0, lo0 + n0)
-    dt0 = time.perf_counter() - t0
-    rows = int(min(dim, max(n0, n0 * target_seconds / max(dt0, 1e-6))))
-    lo = max(0, mid - rows // 2)
-    out = np.zeros(rows)
-    t0 = time.perf_counter()
-    OC.apply(basis, terms, x, out, lo, lo + rows)
-    dt = time.perf_counter() - t0
-    matvec_s = dt * dim / rows
-    return {"value": 1.0 / matvec_s, "unit": "matvec/s", "cores": OC.num_threads(), "kind": "port",
-            "sample": f"rows [{lo},{lo + rows}) of {dim} ({rows / dim:.4%}) timed {dt:.2f}s on {OC.num_threads()} OpenMP threads, "
-                      f"extrapolated to the full matvec; reference-algorithm restatement (oracle/ed_oracle_c.c), not Julia",
-            "seconds_per_matvec_extrapolated": matvec_s, "gnnz_per_s": nnz_eff(n, n_bonds) / matvec_s / 1e9}
+    return CpuReference(w, threads).sample(target_seconds)
 
 
 def run_reference(args, w, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(2.0, min(15.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = max(1.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
+    ref = CpuReference(w)
     vals = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(w, target_seconds=per_step)
+        cb = ref.sample(per_step)
         if i >= args.warmup:
             vals.append(cb["value"])
     v = sum(vals) / len(vals)

@@ -188,3 +188,23 @@ def spin_half_system(n_sites: int):
     site = Site([State("Up", 1), State("Dn", -1)])
     hs = HilbertSpace([site for _ in range(n_sites)])
     return hs, (lambda isite, j: pauli_matrix(hs, isite, j))
+
+
+# ---- term walk on bare bit strings (src/Operator/operator_iterator.jl:34-83); host-side, used for inspection ----
+def get_row_iterator(op: Operator, brow: int):
+    """[(bcol, amplitude)] of row `brow`, in term order: match (b & m) == r -> ((b & ~m) | c, a)."""
+    return [((brow & ~m) | c, a) for (m, r, c, a) in op.terms if (brow & m) == r]
+
+
+def get_column_iterator(op: Operator, bcol: int):
+    """[(brow, amplitude)] of column `bcol`, in term order: match (b & m) == c -> ((b & ~m) | r, a)."""
+    return [((bcol & ~m) | r, a) for (m, r, c, a) in op.terms if (bcol & m) == c]
+
+
+def get_element(op: Operator, br: int, bc: int):
+    """operator_iterator.jl:71-83."""
+    out = 0
+    for (m, r, c, a) in op.terms:
+        if (br & m) == r and ((br & ~m) | c) == bc:
+            out = out + a
+    return out

@@ -109,3 +109,23 @@ def test_lattice_groups_are_groups(ed):
     for op, _ in L.triangular_space_group_irrep(6)[::17]:
         p = ed.symmetry._flatten(op, 36)[0]
         assert {frozenset((p[i], p[j])) for i, j in bonds} == bset
+
+
+def test_term_walk_goldens_on_host_operators(ed, golden):
+    # test/test_operator.jl:302-307, 560-577 through the product's host-side Operator
+    g = golden["pure_iterators"]
+    pop = ed.Operator([tuple(g["term"])])
+    for b, exp in g["row"].items():
+        assert ed.get_row_iterator(pop, int(b)) == [tuple(e) for e in exp]
+    for b, exp in g["col"].items():
+        assert ed.get_column_iterator(pop, int(b)) == [tuple(e) for e in exp]
+    for br, bc, v in g["element"]:
+        assert ed.get_element(pop, br, bc) == v
+    g = golden["sum_iterators"]
+    sop = ed.Operator([tuple(t) for t in g["terms"]])
+    for b, exp in g["row"].items():
+        assert ed.get_row_iterator(sop, int(b)) == [tuple(e) for e in exp]
+    for b, exp in g["col"].items():
+        assert ed.get_column_iterator(sop, int(b)) == [tuple(e) for e in exp]
+    for br, bc, v in g["element"]:
+        assert abs(ed.get_element(sop, br, bc) - v) < 1e-12

@@ -386,6 +386,11 @@ def main():
         peak, peak_src = peaks()
         alg_bytes = 24.0 * n_local     # 8 B basis word + 8 B x + 8 B y per owned row
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if world == 1 and args.kernel == 0 and os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(name, {}).get("dram_bytes_per_launch")
         line = {
             "metric": "H*v matvecs/sec", "value": value, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -399,7 +404,8 @@ def main():
                        "kernel": "generic term-walk" if args.kernel == 1 else "auto",
                        "checksum_x_dot_Hx": checksum},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+                         "traffic": traffic, "traffic_source": "ncu --set full capture committed under profiles/ (bytes per launch)" if traffic else None,
+                         "peak_source": peak_src, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8TBs": achieved / 8000.0},
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -26,6 +26,8 @@ WORKLOADS = {
     "xxz_chain_L32_sz0": dict(n=32, kind="xxz", desc="XXZ chain L=32 (Delta=1), Sz=0, periodic, Pauli normalisation"),
     "j1j2_chain_L28_sz0": dict(n=28, kind="j1j2", desc="J1-J2 chain L=28 (J2=0.5), Sz=0"),
     "xxz_chain_L24_sz0": dict(n=24, kind="xxz", desc="XXZ chain L=24, Sz=0 (small, for quick checks)"),
+    "xxz_chain_L28_sz0": dict(n=28, kind="xxz", desc="XXZ chain L=28, Sz=0"),
+    "xxz_chain_L30_sz0": dict(n=30, kind="xxz", desc="XXZ chain L=30, Sz=0"),
     "xxz_chain_L16_sz0": dict(n=16, kind="xxz", desc="Heisenberg chain L=16, Sz=0 (reference CPU-runnable case)"),
     "tri6x6_k0A1_sz0": dict(n=36, kind="tri", desc="6x6 triangular Heisenberg, T x| C6v k=0 A1, Sz=0: reduced matvec (ComplexF64), |G|=432"),
 }

@@ -283,7 +283,7 @@ struct U1Dispatch<VecT, THREADS, R, -1> {
 
 // One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
 template <typename VecT, int THREADS, int R>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, (R <= 7 && sizeof(VecT) == 8) ? 3 : 2)
 k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
@@ -784,7 +784,11 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
     if (plan->partials.n < (size_t)2 * plan->n_tiles) plan->partials.alloc((size_t)2 * plan->n_tiles);
     partials = plan->partials.p;
   }
-  if (dtype == ED_F64) launch_u1<double, 13>(plan, P, n_launch, out, partials);
+  // rows per thread and pass: 7 (40 registers, 3 CTAs/SM) measured 8.94 ms vs 9.11 ms for 13 (64 registers, 2 CTAs/SM)
+  static const int r_f64 = getenv("EDCUDA_U1_R") ? atoi(getenv("EDCUDA_U1_R")) : 7;
+  if (dtype == ED_F64 && r_f64 == 7) launch_u1<double, 7>(plan, P, n_launch, out, partials);
+  else if (dtype == ED_F64 && r_f64 == 5) launch_u1<double, 5>(plan, P, n_launch, out, partials);
+  else if (dtype == ED_F64) launch_u1<double, 13>(plan, P, n_launch, out, partials);
   else launch_u1<c128, 7>(plan, P, n_launch, out, partials);
   if (alpha_dot) ed_reduce_pairs(partials, n_launch, alpha_dot);
 }

@@ -193,29 +193,31 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     }
     vec_fma(acc_t, a, vt);
   }
-  // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers.
-  // Each slab runs exactly the slot count of its own 32-row group (warp-uniform), SL slots in flight at a time.
+  // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers
 #pragma unroll 1
   for (int c = 0; c < P.n_ll; ++c) {
     const uint8_t* cnt = P.ell_cnt[c] + T.gofs;
-    const uint16_t* e0 = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
+    int nmax = (int)__ldg(cnt + (it >> 5));
+#pragma unroll
+    for (int r = 0; r < NF; ++r) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // warp-uniform
+    const uint16_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
     const double a = P.ll_amp[c];
-    constexpr int SL = 5;
-#pragma unroll
-    for (int r = 0; r <= NF; ++r) {
-      const uint32_t i = r < NF ? (uint32_t)(tid + r * THREADS) : it;
-      const int n = (int)__ldg(cnt + (i >> 5));
-      const uint16_t* e = e0 + i;
-      VecT part = vzero((VecT*)nullptr);
 #pragma unroll 1
-      for (int sl = 0; sl < n; sl += SL) {
-        uint32_t j[SL];
+    for (int sl = 0; sl < nmax; ++sl) {
+      const uint16_t* et = e + tid;
+      const uint32_t jt = __ldg(e + it);
 #pragma unroll
-        for (int q = 0; q < SL; ++q) j[q] = (sl + q < n) ? (uint32_t)__ldg(e + (size_t)(sl + q) * size) : size;   // xs[size] == 0
+      for (int r0 = 0; r0 < NF; r0 += CH) {
+        uint32_t j[CH];
 #pragma unroll
-        for (int q = 0; q < SL; ++q) vec_fma(part, a, xs[j[q]]);
+        for (int cc = 0; cc < CH; ++cc)
+          if (r0 + cc < NF) j[cc] = __ldg(et + (r0 + cc) * THREADS);
+#pragma unroll
+        for (int cc = 0; cc < CH; ++cc)
+          if (r0 + cc < NF) vec_fma(acc[r0 + cc], a, xs[j[cc]]);
       }
-      if (r < NF) acc[r < NF ? r : 0] = vec_add(acc[r < NF ? r : 0], part); else acc_t = vec_add(acc_t, part);
+      vec_fma(acc_t, a, xs[jt]);
+      e += size;
     }
   }
   // bonds straddling bit k: tabulated local column inside the neighbouring tile (0xFFFF = does not fire)

@@ -210,6 +210,8 @@ struct SymDev {
   int n_chunks = 0;        // ceil(bits / 8)
   uint64_t fullmask = 0;
   DevBuf<uint64_t> lut;    // [(g*n_chunks + c)*256 + byte] -> image bits (flip already folded in chunk 0.. see symmetry.cu)
+  DevBuf<uint8_t> tgt_bit;   // [g][64] target position of every bit (reduced_linear.cu)
+  DevBuf<uint64_t> flipmask; // [g] fullmask when the element carries a GlobalBitFlip, else 0
   int n_chunks6 = 0;       // ceil(bits / 6)
   DevBuf<uint64_t> lut6;   // [(g*n_chunks6 + c)*64 + v]: the same action in 6-bit chunks (shared-memory streaming, reduced_staged.cu)
   DevBuf<double> chi;      // [n_ops][2]
@@ -298,6 +300,8 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
                       double* alpha_dot);
+bool ed_apply_reduced_linear_supported(ed_oprep* o);                                            // reduced_linear.cu
+void ed_apply_reduced_linear(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);
 bool ed_apply_reduced_staged_supported(ed_oprep* o);                                            // reduced_staged.cu
 void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);                                                       // reduced.cu (K6)
 void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot);

@@ -81,6 +81,12 @@ k6_apply_reduced(LookupDesc L, SymDesc S, RLookupDesc R, int64_t row_lo, int64_t
 
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot) {
   // large row ranges: word-parallel orbit sweep (reduced_staged.cu); small ones: the simple row-per-thread kernel below
+  // opt-in experiment: warp-per-row kernel exploiting g(b xor f) = g(b) xor g(f) (reduced_linear.cu); default for
+  // large row ranges: the staged word-parallel sweep (reduced_staged.cu); else the simple row-per-thread kernel below
+  if (ed_apply_reduced_linear_supported(o)) {
+    ed_apply_reduced_linear(o, out, x, side, accumulate, alpha_dot);
+    return;
+  }
   static const bool force_simple = getenv("EDCUDA_K6_SIMPLE") != nullptr;
   if (!force_simple && ed_apply_reduced_staged_supported(o)) {
     ed_apply_reduced_staged(o, out, x, side, accumulate, alpha_dot);

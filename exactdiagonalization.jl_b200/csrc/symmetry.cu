@@ -100,6 +100,19 @@ void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, 
       }
     }
   }
+  // bit-level target table + flip masks for the linear (warp-per-row) reduced apply
+  std::vector<uint8_t> tgt_bit((size_t)G * 64, 0);
+  std::vector<uint64_t> flipmask(G, 0);
+  for (int g = 0; g < G; ++g) {
+    for (int bit = 0; bit < 64; ++bit) tgt_bit[(size_t)g * 64 + bit] = (uint8_t)bit;
+    for (int i = 0; i < n; ++i) {
+      int j = sym.perm[(size_t)g * n + i];
+      for (int k = 0; k < space.width[i]; ++k) tgt_bit[(size_t)g * 64 + space.offset[i] + k] = (uint8_t)(space.offset[j] + k);
+    }
+    flipmask[g] = sym.flip[g] ? space.fullmask() : 0ull;
+  }
+  out->tgt_bit.upload(tgt_bit);
+  out->flipmask.upload(flipmask);
   out->n_chunks6 = n_chunks6;
   out->lut6.upload(lut6);
   out->n_ops = G;

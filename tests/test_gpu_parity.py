@@ -541,9 +541,12 @@ def test_reduced_operator_chain4_golden(gpu_ed, golden):
             ropr.get_element(*bad)
 
 
-@pytest.fixture(params=["simple", "staged"])
+@pytest.fixture(params=["simple", "staged", "linear"])
 def k6_path(request, monkeypatch):
-    """Run the reduced-representation tests through both K6 implementations (row-per-thread / word-parallel staged)."""
+    """Run the reduced-representation tests through all three K6 implementations (row-per-thread / word-parallel
+    staged / experimental warp-per-row linear)."""
+    if request.param == "linear":
+        monkeypatch.setenv("EDCUDA_K6_LINEAR", "1")
     monkeypatch.setenv("EDCUDA_K6_MIN_ROWS", "1" if request.param == "staged" else "1000000000000")
     return request.param
 

@@ -238,6 +238,8 @@ def main():
                     help="N>1: how remote rows of x reach a rank: peer loads over NVLink inside the kernel (p2p) or an NCCL all-gather per matvec")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--lanczos", type=int, default=0,
+                    help="also run this many device-resident Lanczos steps (sharded over the ranks) and report ms/step and the lowest Ritz value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     name = args.workload
@@ -384,6 +386,29 @@ def main():
             e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(dim * 8),
                    "ms_per_step": dt * 1e3, "api": ("P2PShardedMatvec" if p2p else "ShardedMatvec") + ".matvec with per-rank pinned host shards (H2D + exchange + ed_apply_async + D2H)"}
 
+    # ---- optional: K7 Lanczos loop on the same representation (config 5 of BASELINE.json) -----------------------
+    lanczos_info = None
+    p2p_used = p2p
+    if args.lanczos > 0:
+        from edcuda.lanczos import ShardedLanczos
+        if p2p:
+            mv.close()
+        del mv
+        torch.cuda.empty_cache()
+        sl = ShardedLanczos(ed.represent(hsr, h).set_kernel(args.kernel), rank, world, np.float64,
+                            exchange="p2p" if (world > 1 and args.exchange == "p2p" and args.kernel == 0) else "allgather")
+        sl.run(3, seed=1)            # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        res = sl.run(args.lanczos, seed=20260717)
+        barrier()
+        dt = time.perf_counter() - t0
+        lanczos_info = {"steps": int(res.steps), "ms_per_step": 1e3 * dt / max(1, args.lanczos), "lowest_ritz": float(res.ritz[0]) if len(res.ritz) else None,
+                        "e0_per_site_over_4": (float(res.ritz[0]) / (4.0 * n)) if len(res.ritz) else None,
+                        "note": "three-term Lanczos, unnormalised device-resident Krylov vectors, fused <u,Hu> and update+norm kernels; scalars all-reduced over NCCL"}
+        if sl.p2p:
+            sl.mv.close()
+        p2p = False
     if rank == 0:
         peak, peak_src = peaks()
         alg_bytes = 24.0 * n_local     # 8 B basis word + 8 B x + 8 B y per owned row
@@ -401,7 +426,7 @@ def main():
             "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": dim, "n_terms": len(h.terms),
                        "rows_per_gpu": n_local, "sharding": "rows" if world > 1 else "none",
                        "exchange": ("none" if world == 1 else "peer loads of far-bond tiles over NVLink inside the kernel (CUDA IPC), "
-                                    "stream-ordered NCCL fence per matvec" if p2p else "nccl all_gather of x per matvec"),
+                                    "stream-ordered NCCL fence per matvec" if p2p_used else "nccl all_gather of x per matvec"),
                        "l2": "inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (dim * 8 / 1e9),
                        "kernel": "generic term-walk" if args.kernel == 1 else "auto",
                        "checksum_x_dot_Hx": checksum},
@@ -413,6 +438,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if lanczos_info is not None:
+            line["lanczos"] = lanczos_info
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w)
         print(json.dumps(line))

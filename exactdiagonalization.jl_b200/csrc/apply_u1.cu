@@ -33,6 +33,7 @@ void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
 #define U1_MAX_HH 192
 #define U1_MAX_MX 64
 #define U1_MAX_MQ 64
+#define U1_MAX_MS 16
 #define ED_MAX_SEG 16
 
 // Everything that depends only on the LOW k bits of a row is tabulated once per plan (tables live in L2):
@@ -55,11 +56,15 @@ struct U1Params {
   const double* dlow;           // [2^k]
   int n_mq; const uint8_t* mq_p; const uint8_t* mq_q; const double* mq_coef;   // n_p n_q terms straddling bit k
   int n_ll; double ll_amp[U1_MAX_CLASSES];
-  const uint16_t* ell[U1_MAX_CLASSES];     // class tables
-  const uint8_t* ell_cnt[U1_MAX_CLASSES];  // slots used per 32-row group
+  const uint32_t* ell[U1_MAX_CLASSES];     // class tables: two consecutive slots per 32-bit word
+  const uint8_t* ell_cnt[U1_MAX_CLASSES];  // slot PAIRS used per 32-row group
   const uint32_t* ell_ofs;                 // [n_ll * (k+1)] start of popcount p inside ell[c]
   int n_hh;   const uint8_t* hh_p; const uint8_t* hh_q; const double* hh_amp;   // exchange bonds inside H
-  int n_mx;   const uint8_t* mx_q; const double* mx_amp; const uint16_t* mx_tab; // straddling exchange bonds
+  int n_mx;   const uint8_t* mx_q; const double* mx_amp; const uint16_t* mx_tab; // straddling exchange bonds (gathered)
+  // straddling bonds whose low site is bit k-1: the firing rows are a contiguous block of the tile and so are their
+  // columns in the neighbour tile -> a shifted coalesced stream like the high-bit bonds
+  int n_ms;   const uint8_t* ms_q; const double* ms_amp;
+  uint32_t ck1[20];             // C(k-1, p)
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
@@ -86,9 +91,9 @@ struct FastU1Plan {
   DevBuf<uint32_t> tile_H, lowofs, grpofs, ell_ofs;
   DevBuf<uint64_t> tile_base;
   DevBuf<uint16_t> lowword, mx_tab;
-  DevBuf<uint8_t> dcode, hh_p, hh_q, mx_q, mq_p, mq_q;
-  DevBuf<double> tile_diag, dval, dlow, hh_amp, mx_amp, mq_coef;
-  std::vector<DevBuf<uint16_t>> ell;
+  DevBuf<uint8_t> dcode, hh_p, hh_q, mx_q, mq_p, mq_q, ms_q;
+  DevBuf<double> tile_diag, dval, dlow, hh_amp, mx_amp, mq_coef, ms_amp;
+  std::vector<DevBuf<uint32_t>> ell;
   std::vector<DevBuf<uint8_t>> ell_cnt;
   DevBuf<double> partials;
   std::vector<uint64_t> h_base, h_size;  // per non-empty tile, ascending
@@ -115,6 +120,7 @@ struct U1Tile {
   VecT* xs;
   const double* hh_amp; const VecT* const* hh_ptr; int n_hh;      // neighbour tiles as resolved pointers
   const double* mx_amp; const VecT* const* mx_ptr; const uint32_t* mx_toff; int n_mx;
+  const double* ms_amp; const VecT* const* ms_ptr; const uint32_t* ms_lo; const uint32_t* ms_len; int n_ms;
   const double* mq_coef; const uint32_t* mq_bit; int n_mq;
   const double* s_dval;
   uint32_t lofs, gofs, size;
@@ -193,6 +199,26 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     }
     vec_fma(acc_t, a, vt);
   }
+  // straddling bonds on bit k-1: a contiguous block of rows reads a shifted stream of the neighbour tile
+#pragma unroll 1
+  for (int e = 0; e < T.n_ms; ++e) {
+    const double a = T.ms_amp[e];
+    const VecT* xe = T.ms_ptr[e];            // already offset: column = row index
+    const uint32_t lo = T.ms_lo[e], len = T.ms_len[e];
+    const VecT* xt = xe + tid;
+    const VecT vt = (it - lo < len) ? ldg_val(xe + it) : vzero((VecT*)nullptr);
+#pragma unroll
+    for (int r0 = 0; r0 < NF; r0 += CH) {
+      VecT v[CH];
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) v[c] = ((uint32_t)(tid + (r0 + c) * THREADS) - lo < len) ? ldg_val(xt + (r0 + c) * THREADS) : vzero((VecT*)nullptr);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+    }
+    vec_fma(acc_t, a, vt);
+  }
   // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers
 #pragma unroll 1
   for (int c = 0; c < P.n_ll; ++c) {
@@ -200,11 +226,11 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     int nmax = (int)__ldg(cnt + (it >> 5));
 #pragma unroll
     for (int r = 0; r < NF; ++r) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // warp-uniform
-    const uint16_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
+    const uint32_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
     const double a = P.ll_amp[c];
 #pragma unroll 1
-    for (int sl = 0; sl < nmax; ++sl) {
-      const uint16_t* et = e + tid;
+    for (int sl = 0; sl < nmax; ++sl) {     // one iteration = a PAIR of slots packed in one 32-bit word
+      const uint32_t* et = e + tid;
       const uint32_t jt = __ldg(e + it);
 #pragma unroll
       for (int r0 = 0; r0 < NF; r0 += CH) {
@@ -214,9 +240,10 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
           if (r0 + cc < NF) j[cc] = __ldg(et + (r0 + cc) * THREADS);
 #pragma unroll
         for (int cc = 0; cc < CH; ++cc)
-          if (r0 + cc < NF) vec_fma(acc[r0 + cc], a, xs[j[cc]]);
+          if (r0 + cc < NF) { vec_fma(acc[r0 + cc], a, xs[j[cc] & 0xFFFFu]); vec_fma(acc[r0 + cc], a, xs[j[cc] >> 16]); }
       }
-      vec_fma(acc_t, a, xs[jt]);
+      vec_fma(acc_t, a, xs[jt & 0xFFFFu]);
+      vec_fma(acc_t, a, xs[jt >> 16]);
       e += size;
     }
   }
@@ -295,6 +322,10 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   const VecT** mx_ptr = hh_ptr + U1_MAX_HH;
   uint32_t* mx_toff = reinterpret_cast<uint32_t*>(mx_ptr + U1_MAX_MX);
   uint32_t* mq_bit = mx_toff + U1_MAX_MX;
+  uint32_t* ms_lo = mq_bit + U1_MAX_MQ;
+  uint32_t* ms_len = ms_lo + U1_MAX_MS;
+  double* ms_amp = reinterpret_cast<double*>(ms_len + U1_MAX_MS);
+  const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + U1_MAX_MS);
   __shared__ int s_counts[2];
 
   const int tid = threadIdx.x;
@@ -335,6 +366,18 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       mx_amp[b] = P.mx_amp[b];
       mx_toff[b] = ((uint32_t)(2 * b + hbit) << k) + lofs;
     }
+    for (int b = lane; b < P.n_ms; b += 32) {
+      const int q = P.ms_q[b];
+      const uint32_t hbit = (H >> q) & 1u;
+      const VecT* xn = u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)]);
+      const uint32_t n0 = P.ck1[p_low];                  // rows of this tile whose bit k-1 is clear (they come first)
+      if (hbit == 0) {                                   // rows with bit k-1 set -> first rows of the neighbour (p_low - 1)
+        ms_lo[b] = n0; ms_len[b] = size - n0; ms_ptr[b] = xn - n0;
+      } else {                                           // rows with bit k-1 clear -> last rows of the neighbour (p_low + 1)
+        ms_lo[b] = 0; ms_len[b] = n0; ms_ptr[b] = xn + P.ck1[p_low + 1];
+      }
+      ms_amp[b] = P.ms_amp[b];
+    }
   } else if (tid < 96) {
     const int lane = tid - 64;
     int n = 0;
@@ -363,6 +406,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   T.xs = xs;
   T.hh_amp = hh_amp; T.hh_ptr = hh_ptr; T.n_hh = s_counts[0];
   T.mx_amp = mx_amp; T.mx_ptr = mx_ptr; T.mx_toff = mx_toff; T.n_mx = P.n_mx;
+  T.ms_amp = ms_amp; T.ms_ptr = ms_ptr; T.ms_lo = ms_lo; T.ms_len = ms_len; T.n_ms = P.n_ms;
   T.mq_coef = mq_coef; T.mq_bit = mq_bit; T.n_mq = s_counts[1];
   T.s_dval = s_dval;
   T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = (int64_t)base;
@@ -576,8 +620,8 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   }
 
   // ---- exchange bonds: split at bit k --------------------------------------------------------------------
-  std::vector<uint8_t> hh_p, hh_q, mx_p, mx_q;
-  std::vector<double> hh_amp, mx_amp;
+  std::vector<uint8_t> hh_p, hh_q, mx_p, mx_q, ms_q;
+  std::vector<double> hh_amp, mx_amp, ms_amp;
   struct LL { int d; uint32_t mask; double amp; };
   std::vector<LL> lls;
   for (auto& c : L.exch) {
@@ -587,6 +631,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
       const int q = p + c.d;
       if (q < k) ll |= 1ull << p;
       else if (p >= k) { hh_p.push_back((uint8_t)(p - k)); hh_q.push_back((uint8_t)(q - k)); hh_amp.push_back(c.v); }
+      else if (p == k - 1) { ms_q.push_back((uint8_t)(q - k)); ms_amp.push_back(c.v); }   // contiguous block form
       else { mx_p.push_back((uint8_t)p); mx_q.push_back((uint8_t)(q - k)); mx_amp.push_back(c.v); }
     }
     if (ll) lls.push_back({c.d, (uint32_t)(ll & lowmask), c.v});
@@ -595,7 +640,9 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   std::map<double, std::vector<LL>> by_amp;
   for (auto& l : lls) by_amp[l.amp].push_back(l);
   if ((int)by_amp.size() > U1_MAX_CLASSES) return plan;
-  if ((int)hh_p.size() > U1_MAX_HH || (int)mx_p.size() > U1_MAX_MX) return plan;
+  if ((int)hh_p.size() > U1_MAX_HH || (int)mx_p.size() > U1_MAX_MX || (int)ms_q.size() > U1_MAX_MS) return plan;
+  P.n_ms = (int)ms_q.size();
+  for (int p = 0; p < 20; ++p) P.ck1[p] = (uint32_t)binom_u64(k - 1, p);
   P.n_hh = (int)hh_p.size();
   P.n_mx = (int)mx_p.size();
   P.n_ll = (int)by_amp.size();
@@ -607,7 +654,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
     std::vector<uint16_t> nb;
     for (auto& kv : by_amp) {
       P.ll_amp[c] = kv.first;
-      std::vector<uint16_t> table;
+      std::vector<uint32_t> table;      // two consecutive slots per word
       std::vector<uint8_t> cnt(grpofs[k + 1], 0);
       for (int p = 0; p <= k; ++p) {
         const uint32_t size = lowofs[p + 1] - lowofs[p];
@@ -628,13 +675,18 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
           }
           maxslot = std::max<uint32_t>(maxslot, (uint32_t)lists[i].size());
           uint8_t& g = cnt[grpofs[p] + i / 32];
-          g = std::max<uint8_t>(g, (uint8_t)lists[i].size());
+          g = std::max<uint8_t>(g, (uint8_t)((lists[i].size() + 1) / 2));
         }
+        const uint32_t maxpair = (maxslot + 1) / 2;
         ell_ofs[(size_t)c * (k + 1) + p] = (uint32_t)table.size();
         const size_t start = table.size();
-        table.resize(start + (size_t)maxslot * size, (uint16_t)size);   // padding -> xs[size] == 0
+        table.resize(start + (size_t)maxpair * size, (uint32_t)size | ((uint32_t)size << 16));   // padding -> xs[size] == 0
         for (uint32_t i = 0; i < size; ++i)
-          for (size_t sl = 0; sl < lists[i].size(); ++sl) table[start + sl * size + i] = lists[i][sl];
+          for (size_t sl = 0; sl < lists[i].size(); ++sl) {
+            uint32_t& wd = table[start + (sl / 2) * size + i];
+            if (sl & 1) wd = (wd & 0x0000FFFFu) | ((uint32_t)lists[i][sl] << 16);
+            else wd = (wd & 0xFFFF0000u) | lists[i][sl];
+          }
       }
       if (table.empty()) table.push_back(0);
       plan->ell[c].upload(table);
@@ -673,8 +725,8 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
 
   auto nonempty8 = [](std::vector<uint8_t>& v) { if (v.empty()) v.push_back(0); };
   auto nonemptyd = [](std::vector<double>& v) { if (v.empty()) v.push_back(0.0); };
-  nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q);
-  nonemptyd(hh_amp); nonemptyd(mx_amp); nonemptyd(mq_coef); nonemptyd(dval);
+  nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q); nonempty8(ms_q);
+  nonemptyd(hh_amp); nonemptyd(mx_amp); nonemptyd(mq_coef); nonemptyd(dval); nonemptyd(ms_amp);
   plan->tile_H.upload(tile_H); plan->tile_base.upload(tile_base); plan->tile_diag.upload(tile_diag);
   plan->lowword.upload(lowword); plan->lowofs.upload(lowofs); plan->grpofs.upload(grpofs);
   plan->dcode.upload(dcode); plan->dval.upload(dval); plan->dlow.upload(dlow);
@@ -682,6 +734,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   plan->ell_ofs.upload(ell_ofs);
   plan->hh_p.upload(hh_p); plan->hh_q.upload(hh_q); plan->hh_amp.upload(hh_amp);
   plan->mx_q.upload(mx_q); plan->mx_amp.upload(mx_amp); plan->mx_tab.upload(mx_tab);
+  plan->ms_q.upload(ms_q); plan->ms_amp.upload(ms_amp);
   ED_CUDA(cudaStreamSynchronize(ed_stream()));
   P.tile_H = plan->tile_H.p; P.tile_base = plan->tile_base.p; P.tile_diag = plan->tile_diag.p;
   P.lowword = plan->lowword.p; P.lowofs = plan->lowofs.p; P.grpofs = plan->grpofs.p;
@@ -691,8 +744,9 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   for (int c = 0; c < P.n_ll; ++c) { P.ell[c] = plan->ell[c].p; P.ell_cnt[c] = plan->ell_cnt[c].p; }
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
   P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
+  P.ms_q = plan->ms_q.p; P.ms_amp = plan->ms_amp.p;
   plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
-                     (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4;
+                     (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4 + U1_MAX_MS * (4 + 4 + 8 + 8);
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
   plan->supported = true;
   return plan;

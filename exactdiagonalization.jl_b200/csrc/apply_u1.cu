@@ -55,6 +55,9 @@ struct U1Params {
   const double* dval;           // [256]
   const double* dlow;           // [2^k]
   int n_mq; const uint8_t* mq_p; const uint8_t* mq_q; const double* mq_coef;   // n_p n_q terms straddling bit k
+  // mq_folded: the u8 code also enumerates the low bits the straddling terms look at (dpat = those bits per code,
+  // mq_pidx = which pattern bit a term reads), so the per-tile value table absorbs them and rows need no extra work
+  int mq_folded; const uint8_t* dpat; const uint8_t* mq_pidx;
   int n_ll; double ll_amp[U1_MAX_CLASSES];
   const uint32_t* ell[U1_MAX_CLASSES];     // class tables: two consecutive slots per 32-bit word
   const uint8_t* ell_cnt[U1_MAX_CLASSES];  // slot PAIRS used per 32-row group
@@ -68,6 +71,7 @@ struct U1Params {
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
+  const uint32_t* tile_order;   // optional launch order (whole-basis launches): position -> index into tile_H
   // x as up to ED_MAX_SEG contiguous, tile-aligned segments (local memory or peer GPUs' memory mapped over NVLink)
   int n_seg;
   int64_t seg_lo[ED_MAX_SEG + 1];
@@ -91,12 +95,14 @@ struct FastU1Plan {
   DevBuf<uint32_t> tile_H, lowofs, grpofs, ell_ofs;
   DevBuf<uint64_t> tile_base;
   DevBuf<uint16_t> lowword, mx_tab;
-  DevBuf<uint8_t> dcode, hh_p, hh_q, mx_q, mq_p, mq_q, ms_q;
+  DevBuf<uint8_t> dcode, hh_p, hh_q, mx_q, mq_p, mq_q, ms_q, dpat, mq_pidx;
+  DevBuf<uint32_t> tile_order;
   DevBuf<double> tile_diag, dval, dlow, hh_amp, mx_amp, mq_coef, ms_amp;
   std::vector<DevBuf<uint32_t>> ell;
   std::vector<DevBuf<uint8_t>> ell_cnt;
   DevBuf<double> partials;
   std::vector<uint64_t> h_base, h_size;  // per non-empty tile, ascending
+  bool order_on = false;
 };
 
 template <typename T>
@@ -329,7 +335,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   __shared__ int s_counts[2];
 
   const int tid = threadIdx.x;
-  const uint32_t H = P.tile_H[P.tile_first + blockIdx.x];
+  const uint32_t H = P.tile_H[P.tile_order ? P.tile_order[blockIdx.x] : P.tile_first + blockIdx.x];
   const int p_low = P.n_set - __popc(H);
   const uint32_t lofs = P.lowofs[p_low];
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
@@ -381,7 +387,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   } else if (tid < 96) {
     const int lane = tid - 64;
     int n = 0;
-    for (int b0 = 0; b0 < P.n_mq; b0 += 32) {
+    for (int b0 = 0; b0 < P.n_mq && !P.mq_folded; b0 += 32) {
       const int b = b0 + lane;
       const bool on = b < P.n_mq && ((H >> P.mq_q[b]) & 1u);
       const unsigned m = __ballot_sync(0xffffffffu, on);
@@ -394,7 +400,17 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
     }
     if (lane == 0) s_counts[1] = n;
   }
-  if (P.diag_mode == 1) for (int i = tid; i < 256; i += THREADS) s_dval[i] = P.dval[i];
+  if (P.diag_mode == 1) {
+    for (int i = tid; i < 256; i += THREADS) {
+      double v = P.dval[i];
+      if (P.mq_folded) {
+        const uint32_t pat = P.dpat[i];
+        for (int e = 0; e < P.n_mq; ++e)
+          if (((H >> P.mq_q[e]) & 1u) && ((pat >> P.mq_pidx[e]) & 1u)) v += P.mq_coef[e];
+      }
+      s_dval[i] = v;
+    }
+  }
   {
     const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
@@ -599,24 +615,59 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   if ((int)mq_p.size() > U1_MAX_MQ) return plan;
   P.n_mq = (int)mq_p.size();
   std::vector<double> dval;
-  std::vector<uint8_t> dcode(nlow, 0);
-  if (!any_low_diag) P.diag_mode = 0;
-  else {
-    std::map<double, int> codes;
-    bool fits = true;
-    for (uint32_t i = 0; i < nlow && fits; ++i) {
-      auto it = codes.find(dlow[i]);
-      if (it == codes.end()) {
-        if (codes.size() >= 256) { fits = false; break; }
-        it = codes.emplace(dlow[i], (int)codes.size()).first;
+  std::vector<uint8_t> dcode(nlow, 0), dpat(256, 0), mq_pidx;
+  P.mq_folded = 0;
+  {
+    // low sites the straddling n_p n_q terms look at; when (low diagonal value, those bits) takes <= 256 distinct
+    // values the u8 code enumerates the pairs and the kernel folds the straddling terms into its per-tile value table
+    std::vector<int> pm;
+    for (uint8_t pp : mq_p) if (std::find(pm.begin(), pm.end(), (int)pp) == pm.end()) pm.push_back(pp);
+    bool folded = false;
+    if (!mq_p.empty() && pm.size() <= 8 && !getenv("EDCUDA_U1_NOFOLD")) {
+      std::map<std::pair<double, uint32_t>, int> codes;
+      bool fits = true;
+      for (uint32_t i = 0; i < nlow && fits; ++i) {
+        const uint32_t w = lowword[i];
+        uint32_t pat = 0;
+        for (size_t j = 0; j < pm.size(); ++j) pat |= ((w >> pm[j]) & 1u) << j;
+        auto key = std::make_pair(dlow[i], pat);
+        auto it = codes.find(key);
+        if (it == codes.end()) {
+          if (codes.size() >= 256) { fits = false; break; }
+          it = codes.emplace(key, (int)codes.size()).first;
+        }
+        dcode[i] = (uint8_t)it->second;
       }
-      dcode[i] = (uint8_t)it->second;
+      if (fits) {
+        folded = true;
+        P.diag_mode = 1;
+        P.mq_folded = 1;
+        dval.assign(256, 0.0);
+        for (auto& kv : codes) { dval[kv.second] = kv.first.first; dpat[kv.second] = (uint8_t)kv.first.second; }
+        for (uint8_t pp : mq_p) mq_pidx.push_back((uint8_t)(std::find(pm.begin(), pm.end(), (int)pp) - pm.begin()));
+      }
     }
-    if (fits) {
-      P.diag_mode = 1;
-      dval.assign(256, 0.0);
-      for (auto& kv : codes) dval[kv.second] = kv.first;
-    } else P.diag_mode = 2;
+    if (!folded) {
+      std::fill(dcode.begin(), dcode.end(), 0);
+      if (!any_low_diag) P.diag_mode = 0;
+      else {
+        std::map<double, int> codes;
+        bool fits = true;
+        for (uint32_t i = 0; i < nlow && fits; ++i) {
+          auto it = codes.find(dlow[i]);
+          if (it == codes.end()) {
+            if (codes.size() >= 256) { fits = false; break; }
+            it = codes.emplace(dlow[i], (int)codes.size()).first;
+          }
+          dcode[i] = (uint8_t)it->second;
+        }
+        if (fits) {
+          P.diag_mode = 1;
+          dval.assign(256, 0.0);
+          for (auto& kv : codes) dval[kv.second] = kv.first;
+        } else P.diag_mode = 2;
+      }
+    }
   }
 
   // ---- exchange bonds: split at bit k --------------------------------------------------------------------
@@ -722,15 +773,31 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   }
   P.tile_cap = tile_cap;
   plan->n_tiles = (int)tile_H.size();
+  // optional launch order for whole-basis launches: tiles grouped by a window of "slow" H bits, so that the tiles
+  // running at the same time are closed under the bonds on the remaining (fast) bits -- including the periodic bond,
+  // whose H bit is the top one -- and find each other's x in L2.  EDCUDA_U1_ORDER="first_slow_bit,n_slow_bits".
+  plan->order_on = false;
+  if (const char* e = getenv("EDCUDA_U1_ORDER")) {
+    int s0 = -1, ns = 0;
+    if (sscanf(e, "%d,%d", &s0, &ns) == 2 && s0 >= 0 && ns > 0 && s0 + ns <= hb) {
+      std::vector<uint32_t> order(tile_H.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
+      const uint32_t smask = ((1u << ns) - 1u) << s0;
+      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (tile_H[a] & smask) < (tile_H[b] & smask); });
+      plan->tile_order.upload(order);
+      plan->order_on = true;
+    }
+  }
 
   auto nonempty8 = [](std::vector<uint8_t>& v) { if (v.empty()) v.push_back(0); };
   auto nonemptyd = [](std::vector<double>& v) { if (v.empty()) v.push_back(0.0); };
-  nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q); nonempty8(ms_q);
+  nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q); nonempty8(ms_q); nonempty8(mq_pidx);
   nonemptyd(hh_amp); nonemptyd(mx_amp); nonemptyd(mq_coef); nonemptyd(dval); nonemptyd(ms_amp);
   plan->tile_H.upload(tile_H); plan->tile_base.upload(tile_base); plan->tile_diag.upload(tile_diag);
   plan->lowword.upload(lowword); plan->lowofs.upload(lowofs); plan->grpofs.upload(grpofs);
   plan->dcode.upload(dcode); plan->dval.upload(dval); plan->dlow.upload(dlow);
   plan->mq_p.upload(mq_p); plan->mq_q.upload(mq_q); plan->mq_coef.upload(mq_coef);
+  plan->dpat.upload(dpat); plan->mq_pidx.upload(mq_pidx);
   plan->ell_ofs.upload(ell_ofs);
   plan->hh_p.upload(hh_p); plan->hh_q.upload(hh_q); plan->hh_amp.upload(hh_amp);
   plan->mx_q.upload(mx_q); plan->mx_amp.upload(mx_amp); plan->mx_tab.upload(mx_tab);
@@ -740,6 +807,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   P.lowword = plan->lowword.p; P.lowofs = plan->lowofs.p; P.grpofs = plan->grpofs.p;
   P.dcode = plan->dcode.p; P.dval = plan->dval.p; P.dlow = plan->dlow.p;
   P.mq_p = plan->mq_p.p; P.mq_q = plan->mq_q.p; P.mq_coef = plan->mq_coef.p;
+  P.dpat = plan->dpat.p; P.mq_pidx = plan->mq_pidx.p;
   P.ell_ofs = plan->ell_ofs.p;
   for (int c = 0; c < P.n_ll; ++c) { P.ell[c] = plan->ell[c].p; P.ell_cnt[c] = plan->ell_cnt[c].p; }
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
@@ -806,6 +874,14 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   P.row_lo = o->row_lo;
   P.row_hi = o->row_hi;
   P.accumulate = accumulate;
+  // profiling knob (results are WRONG when set): drop parts of the kernel to measure what each costs
+  static const int ablate = getenv("EDCUDA_U1_ABLATE") ? atoi(getenv("EDCUDA_U1_ABLATE")) : 0;
+  if (ablate & 1) P.n_ll = 0;
+  if (ablate & 2) P.n_hh = 0;
+  if (ablate & 4) P.n_mx = 0;
+  if (ablate & 8) P.n_ms = 0;
+  if (ablate & 16) P.n_mq = 0;
+  if (ablate & 32) P.diag_mode = 0;
   if (o->x_seg_ptr.empty()) {
     ED_REQUIRE(x != nullptr, ED_ERR_ARGUMENT, "null input vector");
     P.n_seg = 1;
@@ -829,6 +905,7 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   int last = (int)(std::lower_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)o->row_hi) - plan->h_base.begin());
   const int n_launch = last - first;
   P.tile_first = first;
+  P.tile_order = (plan->order_on && first == 0 && n_launch == plan->n_tiles) ? plan->tile_order.p : nullptr;
   if (n_launch <= 0 || o->row_hi <= o->row_lo) {
     if (alpha_dot) ED_CUDA(cudaMemsetAsync(alpha_dot, 0, 2 * sizeof(double), ed_stream()));
     return;

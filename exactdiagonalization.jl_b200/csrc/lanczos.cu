@@ -16,30 +16,22 @@
 
 void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
 
-template <typename VecT>
-__global__ void __launch_bounds__(256)
-k7_lanczos_update(VecT* __restrict__ u_prev_inout, const VecT* __restrict__ w, const VecT* __restrict__ u_cur, int64_t n,
-                  const double* __restrict__ dot, const double* __restrict__ norm2_cur,
-                  const double* __restrict__ norm2_prev, double* __restrict__ partials) {
+// Lanczos coefficients from the device-resident scalars (see the header comment)
+__device__ __forceinline__ void k7_coefs(const double* dot, const double* norm2_cur, const double* norm2_prev,
+                                         double& c1, double& c2, double& c3) {
   const double n2c = *norm2_cur;
   const double nc = sqrt(n2c);
   const double alpha = dot[0] / n2c;
-  const double c1 = 1.0 / nc;
-  const double c2 = alpha / nc;
-  double c3 = 0.0;
+  c1 = 1.0 / nc;
+  c2 = alpha / nc;
+  c3 = 0.0;
   if (norm2_prev) {
     const double n2p = *norm2_prev;
     c3 = n2p > 0.0 ? nc / sqrt(n2p) : 0.0;
   }
-  double acc = 0.0, dummy = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    c128 wv = to_c128(w[i]), uc = to_c128(u_cur[i]), up = to_c128(u_prev_inout[i]);
-    c128 r = make_c128(c1 * wv.re - c2 * uc.re - c3 * up.re, c1 * wv.im - c2 * uc.im - c3 * up.im);
-    if (sizeof(VecT) == 16) st_val(reinterpret_cast<c128*>(u_prev_inout) + i, r);
-    else reinterpret_cast<double*>(u_prev_inout)[i] = r.re;
-    acc += r.re * r.re + r.im * r.im;
-  }
-  (void)dummy;
+}
+
+__device__ __forceinline__ void k7_block_reduce(double acc, double* __restrict__ partials) {
   __shared__ double s_red[8];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
@@ -50,6 +42,65 @@ k7_lanczos_update(VecT* __restrict__ u_prev_inout, const VecT* __restrict__ w, c
     partials[2 * blockIdx.x] = a;
     partials[2 * blockIdx.x + 1] = 0.0;
   }
+}
+
+// u_{j+1} = c1 w - c2 u_j - c3 u_{j-1} over a flat array of doubles (a ComplexF64 vector is 2n doubles: the update is
+// component-wise and |r|^2 = re^2 + im^2), 32 B/row of traffic.  Pure streaming: every thread keeps U 16-byte loads per
+// array in flight (Little's law on HBM3e needs > 40 KB in flight per SM); w is dead afterwards -> evict-first loads.
+template <int U>
+__global__ void __launch_bounds__(256)
+k7_lanczos_update_vec(double2* __restrict__ u_prev_inout, const double2* __restrict__ w, const double2* __restrict__ u_cur,
+                      int64_t n2, double* __restrict__ tail_prev, const double* __restrict__ tail_w, const double* __restrict__ tail_cur,
+                      const double* __restrict__ dot, const double* __restrict__ norm2_cur,
+                      const double* __restrict__ norm2_prev, double* __restrict__ partials) {
+  double c1, c2, c3;
+  k7_coefs(dot, norm2_cur, norm2_prev, c1, c2, c3);
+  double acc = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < n2; i += U * stride) {
+    double2 wv[U], uc[U], up[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) { wv[k] = __ldcs(w + i + k * stride); uc[k] = __ldg(u_cur + i + k * stride); up[k] = __ldcs(u_prev_inout + i + k * stride); }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      double2 r;
+      r.x = c1 * wv[k].x - c2 * uc[k].x - c3 * up[k].x;
+      r.y = c1 * wv[k].y - c2 * uc[k].y - c3 * up[k].y;
+      u_prev_inout[i + k * stride] = r;
+      acc = fma(r.x, r.x, fma(r.y, r.y, acc));
+    }
+  }
+  for (; i < n2; i += stride) {
+    const double2 wv = __ldcs(w + i), uc = __ldg(u_cur + i), up = __ldcs(u_prev_inout + i);
+    double2 r;
+    r.x = c1 * wv.x - c2 * uc.x - c3 * up.x;
+    r.y = c1 * wv.y - c2 * uc.y - c3 * up.y;
+    u_prev_inout[i] = r;
+    acc = fma(r.x, r.x, fma(r.y, r.y, acc));
+  }
+  if (tail_prev && blockIdx.x == 0 && threadIdx.x == 0) {   // odd number of doubles
+    const double r = c1 * *tail_w - c2 * *tail_cur - c3 * *tail_prev;
+    *tail_prev = r;
+    acc = fma(r, r, acc);
+  }
+  k7_block_reduce(acc, partials);
+}
+
+// scalar fallback for vectors that are not 16-byte aligned (views into larger buffers)
+__global__ void __launch_bounds__(256)
+k7_lanczos_update_scalar(double* __restrict__ u_prev_inout, const double* __restrict__ w, const double* __restrict__ u_cur, int64_t n,
+                         const double* __restrict__ dot, const double* __restrict__ norm2_cur,
+                         const double* __restrict__ norm2_prev, double* __restrict__ partials) {
+  double c1, c2, c3;
+  k7_coefs(dot, norm2_cur, norm2_prev, c1, c2, c3);
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double r = c1 * w[i] - c2 * u_cur[i] - c3 * u_prev_inout[i];
+    u_prev_inout[i] = r;
+    acc = fma(r, r, acc);
+  }
+  k7_block_reduce(acc, partials);
 }
 
 template <typename VecT>
@@ -113,14 +164,22 @@ static DevBuf<double>& partial_scratch(int n_blocks) {
 
 static void lanczos_update(void* u_prev_inout, const void* w, const void* u_cur, int64_t n, int dtype, const double* dot,
                            const double* norm2_cur, const double* norm2_prev, double* norm2_out) {
-  const int grid = grid_rows(n);
+  const int64_t nd = dtype == ED_C128 ? 2 * n : n;   // doubles
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nd / 2 + 256 * 4 - 1) / (256 * 4), (int64_t)ed_sm_count() * 8));
   double* partials = partial_scratch(grid).p;
-  if (dtype == ED_C128)
-    ED_LAUNCH(k7_lanczos_update<c128>, grid, 256, 0, reinterpret_cast<c128*>(u_prev_inout), reinterpret_cast<const c128*>(w),
-              reinterpret_cast<const c128*>(u_cur), n, dot, norm2_cur, norm2_prev, partials);
-  else
-    ED_LAUNCH(k7_lanczos_update<double>, grid, 256, 0, reinterpret_cast<double*>(u_prev_inout), reinterpret_cast<const double*>(w),
-              reinterpret_cast<const double*>(u_cur), n, dot, norm2_cur, norm2_prev, partials);
+  const bool aligned = (((uintptr_t)u_prev_inout | (uintptr_t)w | (uintptr_t)u_cur) & 15u) == 0;
+  if (aligned) {
+    double* up = reinterpret_cast<double*>(u_prev_inout);
+    const double* wp = reinterpret_cast<const double*>(w);
+    const double* uc = reinterpret_cast<const double*>(u_cur);
+    const bool odd = (nd & 1) != 0;
+    ED_LAUNCH(k7_lanczos_update_vec<4>, grid, 256, 0, reinterpret_cast<double2*>(up), reinterpret_cast<const double2*>(wp),
+              reinterpret_cast<const double2*>(uc), nd / 2, odd ? up + nd - 1 : nullptr, odd ? wp + nd - 1 : nullptr,
+              odd ? uc + nd - 1 : nullptr, dot, norm2_cur, norm2_prev, partials);
+  } else {
+    ED_LAUNCH(k7_lanczos_update_scalar, grid, 256, 0, reinterpret_cast<double*>(u_prev_inout), reinterpret_cast<const double*>(w),
+              reinterpret_cast<const double*>(u_cur), nd, dot, norm2_cur, norm2_prev, partials);
+  }
   ed_reduce_pairs(partials, grid, norm2_out);
 }
 

@@ -1,0 +1,10 @@
+for a in 0 1 2 4 8 16 32 63 3; do
+  echo "ABLATE=$a"; EDCUDA_U1_ABLATE=$a python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    l=l.strip()
+    if l.startswith('{'):
+        d=json.loads(l); print('  kernel_ms',d['roofline']['kernel_ms'])
+    elif l: print('  ',l[:200])
+"
+done

@@ -62,14 +62,6 @@ struct U1Params {
   const uint32_t* ell[U1_MAX_CLASSES];     // class tables: two consecutive slots per 32-bit word
   const uint8_t* ell_cnt[U1_MAX_CLASSES];  // slot PAIRS used per 32-row group
   const uint32_t* ell_ofs;                 // [n_ll * (k+1)] start of popcount p inside ell[c]
-  // nearest-neighbour exchange bonds inside the low bits (q, q+1): the column of row i is i +- C(q, r_q) with r_q the
-  // number of set bits below q, so no per-row index table is needed at all.  The signed offsets come from two tiny
-  // shared-memory tables: lut_lo[low 8 bits] -> 7 x i8 (bonds 0..6), lut_up[class][word >> 7] -> 8 x i16 (bonds 7..14).
-  int cap_hh, cap_mx, cap_mq, cap_ms, cap_codes;   // shared-memory list capacities of this plan (>= 1, <= U1_MAX_*)
-  int lut_on;
-  const uint64_t* lut_lo;       // [256]
-  const uint4* lut_up;          // [(k + 1) << (k - 7)]
-  double nn_amp[16];
   int n_hh;   const uint8_t* hh_p; const uint8_t* hh_q; const double* hh_amp;   // exchange bonds inside H
   int n_mx;   const uint8_t* mx_q; const double* mx_amp; const uint16_t* mx_tab; // straddling exchange bonds (gathered)
   // straddling bonds whose low site is bit k-1: the firing rows are a contiguous block of the tile and so are their
@@ -80,12 +72,6 @@ struct U1Params {
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
   const uint32_t* tile_order;   // optional launch order (whole-basis launches): position -> index into tile_H
-  // group kernel (k2_apply_u1g): H = (hi << gm) | mid; a CTA owns every tile of one (hi, popcount(mid)) class
-  int gm, gcap, n_codes;
-  const uint32_t* grp;          // [n_groups] (hi << 3) | popcount(mid), ascending
-  int grp_first;
-  uint8_t gcount[8];            // tiles per group of mid popcount c
-  uint8_t gmid[8][8];           // the mid patterns of popcount c, ascending
   // x as up to ED_MAX_SEG contiguous, tile-aligned segments (local memory or peer GPUs' memory mapped over NVLink)
   int n_seg;
   int64_t seg_lo[ED_MAX_SEG + 1];
@@ -111,21 +97,12 @@ struct FastU1Plan {
   DevBuf<uint16_t> lowword, mx_tab;
   DevBuf<uint8_t> dcode, hh_p, hh_q, mx_q, mq_p, mq_q, ms_q, dpat, mq_pidx;
   DevBuf<uint32_t> tile_order;
-  DevBuf<uint64_t> lut_lo;
-  DevBuf<uint4> lut_up;
   DevBuf<double> tile_diag, dval, dlow, hh_amp, mx_amp, mq_coef, ms_amp;
   std::vector<DevBuf<uint32_t>> ell;
   std::vector<DevBuf<uint8_t>> ell_cnt;
   DevBuf<double> partials;
   std::vector<uint64_t> h_base, h_size;  // per non-empty tile, ascending
   bool order_on = false;
-  // group kernel configuration (k2_apply_u1g)
-  bool g_on = false;
-  int g_threads = 512, g_rs = 2;
-  size_t g_smem = 0;
-  DevBuf<uint32_t> grp;
-  std::vector<uint64_t> g_lo, g_hi;      // per group: first row of its first tile, end row of its last tile
-  std::vector<uint64_t> blk_base;        // first row of every non-empty hi block (shard boundaries in group mode)
 };
 
 template <typename T>
@@ -152,7 +129,6 @@ struct U1Tile {
   const double* ms_amp; const VecT* const* ms_ptr; const uint32_t* ms_lo; const uint32_t* ms_len; int n_ms;
   const double* mq_coef; const uint32_t* mq_bit; int n_mq;
   const double* s_dval;
-  const uint64_t* s_lut_lo; const uint4* s_lut_up;
   uint32_t lofs, gofs, size;
   int p_low;
   int64_t base;
@@ -249,35 +225,6 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     }
     vec_fma(acc_t, a, vt);
   }
-  // nearest-neighbour bonds inside the low bits: signed column offsets from the two shared-memory LUTs
-  if (P.lut_on) {
-    const uint16_t* lw = P.lowword + T.lofs;
-    uint32_t wv[NF > 0 ? NF : 1];
-#pragma unroll
-    for (int r = 0; r < NF; ++r) wv[r] = __ldg(lw + tid + r * THREADS);
-    const uint32_t wt = __ldg(lw + it);
-#pragma unroll
-    for (int r = 0; r <= NF; ++r) {
-      const uint32_t w = r < NF ? wv[r < NF ? r : 0] : wt;
-      const VecT* xi = xs + (r < NF ? (uint32_t)(tid + r * THREADS) : it);
-      const uint64_t dl = T.s_lut_lo[w & 0xFFu];
-      const uint4 du = T.s_lut_up[w >> 7];
-      const uint32_t dl0 = (uint32_t)dl, dl1 = (uint32_t)(dl >> 32);
-      VecT a_ = vzero((VecT*)nullptr);
-#pragma unroll
-      for (int j = 0; j < 7; ++j) {
-        const int d = (int)(int8_t)((j < 4 ? dl0 : dl1) >> (8 * (j & 3)));
-        if (d != 0) vec_fma(a_, P.nn_amp[j], xi[d]);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t wd = j < 2 ? du.x : j < 4 ? du.y : j < 6 ? du.z : du.w;
-        const int d = (int)(int16_t)(wd >> (16 * (j & 1)));
-        if (d != 0) vec_fma(a_, P.nn_amp[7 + j], xi[d]);
-      }
-      if (r < NF) acc[r < NF ? r : 0] = vec_add(acc[r < NF ? r : 0], a_); else acc_t = vec_add(acc_t, a_);
-    }
-  }
   // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers
 #pragma unroll 1
   for (int c = 0; c < P.n_ll; ++c) {
@@ -369,24 +316,22 @@ struct U1Dispatch<VecT, THREADS, R, -1> {
 
 // One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
 template <typename VecT, int THREADS, int R>
-__global__ void __launch_bounds__(THREADS, sizeof(VecT) != 8 ? 2 : R <= 5 ? 4 : R <= 7 ? 3 : 2)
+__global__ void __launch_bounds__(THREADS, (R <= 7 && sizeof(VecT) == 8) ? 3 : 2)
 k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
   double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 1);
-  double* mx_amp = hh_amp + P.cap_hh;
-  double* mq_coef = mx_amp + P.cap_mx;
-  double* s_dval = mq_coef + P.cap_mq;
-  const VecT** hh_ptr = reinterpret_cast<const VecT**>(s_dval + P.cap_codes);
-  const VecT** mx_ptr = hh_ptr + P.cap_hh;
-  double* ms_amp = reinterpret_cast<double*>(mx_ptr + P.cap_mx);
-  const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + P.cap_ms);
-  uint32_t* mx_toff = reinterpret_cast<uint32_t*>(ms_ptr + P.cap_ms);
-  uint32_t* mq_bit = mx_toff + P.cap_mx;
-  uint32_t* ms_lo = mq_bit + P.cap_mq;
-  uint32_t* ms_len = ms_lo + P.cap_ms;
-  uint4* s_lut_up = reinterpret_cast<uint4*>(smem_raw + ((reinterpret_cast<unsigned char*>(ms_len + P.cap_ms) - smem_raw + 15) & ~(size_t)15));
-  uint64_t* s_lut_lo = reinterpret_cast<uint64_t*>(s_lut_up + (P.lut_on ? (1u << (P.k - 7)) : 0u));
+  double* mx_amp = hh_amp + U1_MAX_HH;
+  double* mq_coef = mx_amp + U1_MAX_MX;
+  double* s_dval = mq_coef + U1_MAX_MQ;                                // 256
+  const VecT** hh_ptr = reinterpret_cast<const VecT**>(s_dval + 256);
+  const VecT** mx_ptr = hh_ptr + U1_MAX_HH;
+  uint32_t* mx_toff = reinterpret_cast<uint32_t*>(mx_ptr + U1_MAX_MX);
+  uint32_t* mq_bit = mx_toff + U1_MAX_MX;
+  uint32_t* ms_lo = mq_bit + U1_MAX_MQ;
+  uint32_t* ms_len = ms_lo + U1_MAX_MS;
+  double* ms_amp = reinterpret_cast<double*>(ms_len + U1_MAX_MS);
+  const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + U1_MAX_MS);
   __shared__ int s_counts[2];
 
   const int tid = threadIdx.x;
@@ -456,7 +401,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
     if (lane == 0) s_counts[1] = n;
   }
   if (P.diag_mode == 1) {
-    for (int i = tid; i < P.cap_codes; i += THREADS) {
+    for (int i = tid; i < 256; i += THREADS) {
       double v = P.dval[i];
       if (P.mq_folded) {
         const uint32_t pat = P.dpat[i];
@@ -471,17 +416,10 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
   }
   if (tid == 0) xs[size] = vzero((VecT*)nullptr);
-  if (P.lut_on) {
-    const uint32_t nu = 1u << (k - 7);
-    const uint4* src = P.lut_up + (size_t)p_low * nu;
-    for (uint32_t i = tid; i < nu; i += THREADS) s_lut_up[i] = __ldg(src + i);
-    for (uint32_t i = tid; i < 256; i += THREADS) s_lut_lo[i] = __ldg(P.lut_lo + i);
-  }
   __syncthreads();
 
   U1Tile<VecT> T;
   T.xs = xs;
-  T.s_lut_lo = s_lut_lo; T.s_lut_up = s_lut_up;
   T.hh_amp = hh_amp; T.hh_ptr = hh_ptr; T.n_hh = s_counts[0];
   T.mx_amp = mx_amp; T.mx_ptr = mx_ptr; T.mx_toff = mx_toff; T.n_mx = P.n_mx;
   T.ms_amp = ms_amp; T.ms_ptr = ms_ptr; T.ms_lo = ms_lo; T.ms_len = ms_len; T.n_ms = P.n_ms;
@@ -509,361 +447,6 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       for (int w = 0; w < THREADS / 32; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
       dot_partials[2 * blockIdx.x] = a;
       dot_partials[2 * blockIdx.x + 1] = c;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Group kernel.  The plain kernel above is bound by L2 -> SM bandwidth (126 B per row: every x element is fetched ~9
-// times as a neighbour stream and every CTA re-reads the 2-byte ELL column indices of its popcount class).  Here a CTA
-// owns ALL tiles that share their high bits `hi` and the popcount c of the gm "mid" bits just above the low k:
-// C(gm, c) tiles of identical shape.  The ELL indices, diagonal codes and straddler tables are loaded once and applied
-// to every tile of the group (index traffic / C(gm,c)), and the bonds inside the mid bits become conflict-free
-// shared-memory streams between the group's own tiles instead of L2 streams.
-struct U1GLayout {
-  size_t xs, dval, hh_ptr, hh_amp, int_amp, int_src, ms_ptr, ms_amp, ms_lo, ms_len, mx_ptr, mx_amp, mx_toff, dt, base, cnt, total;
-};
-__host__ __device__ inline U1GLayout u1g_layout(int G, uint32_t tile_cap, int vec_bytes, int n_codes, int n_hh, int n_ms, int n_mx) {
-  U1GLayout L;
-  size_t o = 0;
-  auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
-  L.xs = take((size_t)G * (tile_cap + 1) * vec_bytes);
-  L.dval = take((size_t)G * n_codes * 8);
-  L.hh_ptr = take((size_t)G * n_hh * 8);
-  L.hh_amp = take((size_t)G * n_hh * 8);
-  L.int_amp = take((size_t)G * n_hh * 8);
-  L.int_src = take((size_t)G * n_hh * 4);
-  L.ms_ptr = take((size_t)G * n_ms * 8);
-  L.ms_amp = take((size_t)G * n_ms * 8);
-  L.ms_lo = take((size_t)G * n_ms * 4);
-  L.ms_len = take((size_t)G * n_ms * 4);
-  L.mx_ptr = take((size_t)G * n_mx * 8);
-  L.mx_amp = take((size_t)G * n_mx * 8);
-  L.mx_toff = take((size_t)G * n_mx * 4);
-  L.dt = take((size_t)G * 8);
-  L.base = take((size_t)G * 8);
-  L.cnt = take((size_t)G * 2 * 4);
-  L.total = o;
-  return L;
-}
-
-template <typename VecT>
-struct U1GView {
-  VecT* xs; uint32_t xstride;
-  const double* dval; int n_codes;
-  const VecT* const* hh_ptr; const double* hh_amp; const double* int_amp; const uint32_t* int_src;
-  const VecT* const* ms_ptr; const double* ms_amp; const uint32_t* ms_lo; const uint32_t* ms_len;
-  const VecT* const* mx_ptr; const double* mx_amp; const uint32_t* mx_toff;
-  const double* dt; const int64_t* base; const int* cnt;
-  int nh, nms, nmx;
-  uint32_t lofs, gofs, size;
-  int p_low;
-};
-
-// Rows i = tid + slab*THREADS of all G tiles; RS slabs per pass -> G*RS accumulators in registers.
-template <typename VecT, int THREADS, int G, int RS>
-__device__ __forceinline__ void u1g_body(const U1Params& P, const U1GView<VecT>& V, VecT* __restrict__ y, bool want_dot,
-                                         double& dre, double& dim_) {
-  constexpr int CH = (G * RS >= 12) ? 2 : (RS >= 4 ? 2 : 3);   // neighbour streams loaded back to back (x RS rows each)
-  const uint32_t S = V.size;
-  const int n_slab = (int)((S + THREADS - 1) / THREADS);
-#pragma unroll 1
-  for (int s0 = 0; s0 < n_slab; s0 += RS) {
-    if ((threadIdx.x & ~31u) + (uint32_t)s0 * THREADS >= S) break;   // this warp has no rows left (warp-uniform)
-    uint32_t ic[RS];
-    bool ok[RS];
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-      const uint32_t i = threadIdx.x + (uint32_t)(s0 + r) * THREADS;
-      ok[r] = i < S;
-      ic[r] = ok[r] ? i : S - 1;      // clamped: every load stays in bounds, only the store is predicated
-    }
-    VecT acc[G][RS];
-    // diagonal: one u8 code per row (shared by the group), per-tile value tables
-    {
-      uint32_t code[RS];
-#pragma unroll
-      for (int r = 0; r < RS; ++r) code[r] = P.diag_mode == 1 ? (uint32_t)__ldg(P.dcode + V.lofs + ic[r]) : 0u;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const VecT* xg = V.xs + g * V.xstride;
-        const double dtg = V.dt[g];
-        const double* dv = V.dval + g * V.n_codes;
-#pragma unroll
-        for (int r = 0; r < RS; ++r) {
-          const double d = P.diag_mode == 1 ? dtg + dv[code[r]] : dtg;
-          acc[g][r] = vec_scale<VecT>(d, xg[ic[r]]);
-        }
-      }
-    }
-    // exchange bonds inside the low k bits: one index load serves 2 slots x G tiles
-#pragma unroll 1
-    for (int c = 0; c < P.n_ll; ++c) {
-      const uint8_t* cnt = P.ell_cnt[c] + V.gofs;
-      int nmax = 0;
-#pragma unroll
-      for (int r = 0; r < RS; ++r) nmax = max(nmax, (int)__ldg(cnt + (ic[r] >> 5)));
-      const uint32_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + V.p_low];
-      const double a = P.ll_amp[c];
-      uint32_t jn[RS];
-#pragma unroll
-      for (int r = 0; r < RS; ++r) jn[r] = nmax > 0 ? __ldg(e + ic[r]) : 0u;
-#pragma unroll 1
-      for (int sl = 0; sl < nmax; ++sl) {
-        uint32_t j[RS];
-#pragma unroll
-        for (int r = 0; r < RS; ++r) j[r] = jn[r];
-        e += S;
-        if (sl + 1 < nmax) {
-#pragma unroll
-          for (int r = 0; r < RS; ++r) jn[r] = __ldg(e + ic[r]);     // next slot pair in flight during the gathers
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const VecT* xg = V.xs + g * V.xstride;
-#pragma unroll
-          for (int r = 0; r < RS; ++r) {
-            vec_fma(acc[g][r], a, xg[j[r] & 0xFFFFu]);
-            vec_fma(acc[g][r], a, xg[j[r] >> 16]);
-          }
-        }
-      }
-    }
-    // bonds inside the mid bits: the partner tile is in this CTA's shared memory, same local index
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int ni = V.cnt[2 * g + 1];
-#pragma unroll 1
-      for (int t = 0; t < ni; ++t) {
-        const VecT* src = V.xs + V.int_src[g * V.nh + t] * V.xstride;
-        const double a = V.int_amp[g * V.nh + t];
-#pragma unroll
-        for (int r = 0; r < RS; ++r) vec_fma(acc[g][r], a, src[ic[r]]);
-      }
-    }
-    // straddling bonds on bit k-1: contiguous block of rows <-> shifted stream of the neighbour tile
-#pragma unroll 1
-    for (int e = 0; e < P.n_ms; ++e) {
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const double a = V.ms_amp[g * V.nms + e];
-        const VecT* xe = V.ms_ptr[g * V.nms + e];
-        const uint32_t lo = V.ms_lo[g * V.nms + e], len = V.ms_len[g * V.nms + e];
-        VecT v[RS];
-#pragma unroll
-        for (int r = 0; r < RS; ++r) v[r] = (ic[r] - lo < len) ? ldg_val(xe + ic[r]) : vzero((VecT*)nullptr);
-#pragma unroll
-        for (int r = 0; r < RS; ++r) vec_fma(acc[g][r], a, v[r]);
-      }
-    }
-    // other bonds straddling bit k: tabulated local column inside the neighbouring tile (0xFFFF = does not fire)
-#pragma unroll 1
-    for (int e = 0; e < P.n_mx; ++e) {
-      uint32_t j[G][RS];
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const uint16_t* tab = P.mx_tab + V.mx_toff[g * V.nmx + e];
-#pragma unroll
-        for (int r = 0; r < RS; ++r) j[g][r] = __ldg(tab + ic[r]);
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const VecT* xe = V.mx_ptr[g * V.nmx + e];
-        const double a = V.mx_amp[g * V.nmx + e];
-        VecT v[RS];
-#pragma unroll
-        for (int r = 0; r < RS; ++r) v[r] = j[g][r] != 0xFFFFu ? ldg_val(xe + j[g][r]) : vzero((VecT*)nullptr);
-#pragma unroll
-        for (int r = 0; r < RS; ++r) vec_fma(acc[g][r], a, v[r]);
-      }
-    }
-    // bonds with at least one site above the mid bits: same local index in a tile of another group (L2 / HBM streams)
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int ne = V.cnt[2 * g];
-      const VecT* const* pp = V.hh_ptr + g * V.nh;
-      const double* aa = V.hh_amp + g * V.nh;
-#pragma unroll 1
-      for (int e = 0; e < ne; e += CH) {
-        VecT v[CH][RS];
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-          if (e + c < ne) {
-            const VecT* xe = pp[e + c];
-#pragma unroll
-            for (int r = 0; r < RS; ++r) v[c][r] = ldg_val(xe + ic[r]);
-          }
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-          if (e + c < ne) {
-            const double a = aa[e + c];
-#pragma unroll
-            for (int r = 0; r < RS; ++r) vec_fma(acc[g][r], a, v[c][r]);
-          }
-      }
-    }
-    // store (row-owner writes)
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const int64_t b = V.base[g];
-      const VecT* xg = V.xs + g * V.xstride;
-#pragma unroll
-      for (int r = 0; r < RS; ++r) {
-        const int64_t row = b + ic[r];
-        if (!ok[r] || row < P.row_lo || row >= P.row_hi) continue;
-        VecT* dst = y + (row - P.row_lo);
-        VecT out = acc[g][r];
-        if (P.accumulate) out = vec_add(out, *dst);
-        st_stream(dst, out);
-        if (want_dot) dot_acc(dre, dim_, xg[ic[r]], out);
-      }
-    }
-  }
-}
-
-template <typename VecT, int THREADS, int RS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB)
-k2_apply_u1g(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nh = max(P.n_hh, 1), nms = max(P.n_ms, 1), nmx = max(P.n_mx, 1);
-  const U1GLayout L = u1g_layout(P.gcap, P.tile_cap, (int)sizeof(VecT), P.n_codes, nh, nms, nmx);
-  VecT* xs = reinterpret_cast<VecT*>(smem_raw + L.xs);
-  double* s_dval = reinterpret_cast<double*>(smem_raw + L.dval);
-  const VecT** hh_ptr = reinterpret_cast<const VecT**>(smem_raw + L.hh_ptr);
-  double* hh_amp = reinterpret_cast<double*>(smem_raw + L.hh_amp);
-  double* int_amp = reinterpret_cast<double*>(smem_raw + L.int_amp);
-  uint32_t* int_src = reinterpret_cast<uint32_t*>(smem_raw + L.int_src);
-  const VecT** ms_ptr = reinterpret_cast<const VecT**>(smem_raw + L.ms_ptr);
-  double* ms_amp = reinterpret_cast<double*>(smem_raw + L.ms_amp);
-  uint32_t* ms_lo = reinterpret_cast<uint32_t*>(smem_raw + L.ms_lo);
-  uint32_t* ms_len = reinterpret_cast<uint32_t*>(smem_raw + L.ms_len);
-  const VecT** mx_ptr = reinterpret_cast<const VecT**>(smem_raw + L.mx_ptr);
-  double* mx_amp = reinterpret_cast<double*>(smem_raw + L.mx_amp);
-  uint32_t* mx_toff = reinterpret_cast<uint32_t*>(smem_raw + L.mx_toff);
-  double* s_dt = reinterpret_cast<double*>(smem_raw + L.dt);
-  int64_t* s_base = reinterpret_cast<int64_t*>(smem_raw + L.base);
-  int* s_cnt = reinterpret_cast<int*>(smem_raw + L.cnt);
-
-  const int tid = threadIdx.x;
-  const uint32_t gd = P.grp[P.grp_first + blockIdx.x];
-  const uint32_t hi = gd >> 3;
-  const int c = (int)(gd & 7u);
-  const int G = P.gcount[c];
-  const int k = P.k, gm = P.gm;
-  const uint32_t midmask = (1u << gm) - 1u;
-  const int p_low = P.n_set - __popc(hi) - c;
-  const uint32_t lofs = P.lowofs[p_low];
-  const uint32_t size = P.lowofs[p_low + 1] - lofs;
-  const uint32_t xstride = P.tile_cap + 1;
-
-  // ---- prologue: warp g resolves the bond lists of tile g (deterministic ballot compaction) --------------------
-  const int wid = tid >> 5, lane = tid & 31;
-  if (wid < G) {
-    const int g = wid;
-    const uint32_t H = (hi << gm) | P.gmid[c][g];
-    int n_ext = 0, n_int = 0;
-    for (int b0 = 0; b0 < P.n_hh; b0 += 32) {
-      const int b = b0 + lane;
-      bool fire = false, internal = false;
-      uint32_t H2 = 0;
-      if (b < P.n_hh) {
-        const int p = P.hh_p[b], q = P.hh_q[b];
-        fire = (((H >> p) ^ (H >> q)) & 1u) != 0;
-        H2 = H ^ ((1u << p) | (1u << q));
-        internal = fire && p < gm && q < gm;          // both sites in the mid bits: the partner is in this group
-      }
-      const bool ext = fire && !internal;
-      const unsigned me = __ballot_sync(0xffffffffu, ext), mi = __ballot_sync(0xffffffffu, internal);
-      if (ext) {
-        const int slot = n_ext + __popc(me & ((1u << lane) - 1u));
-        hh_ptr[g * nh + slot] = u1_seg_resolve<VecT>(P, P.tile_base[H2]);
-        hh_amp[g * nh + slot] = P.hh_amp[b];
-      }
-      if (internal) {
-        const int slot = n_int + __popc(mi & ((1u << lane) - 1u));
-        const uint32_t mid2 = H2 & midmask;
-        uint32_t g2 = 0;
-        for (int t = 0; t < G; ++t) if (P.gmid[c][t] == mid2) g2 = (uint32_t)t;
-        int_src[g * nh + slot] = g2;
-        int_amp[g * nh + slot] = P.hh_amp[b];
-      }
-      n_ext += __popc(me);
-      n_int += __popc(mi);
-    }
-    for (int b = lane; b < P.n_mx; b += 32) {
-      const int q = P.mx_q[b];
-      const uint32_t hbit = (H >> q) & 1u;
-      mx_ptr[g * nmx + b] = u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)]);
-      mx_amp[g * nmx + b] = P.mx_amp[b];
-      mx_toff[g * nmx + b] = ((uint32_t)(2 * b + hbit) << k) + lofs;
-    }
-    for (int b = lane; b < P.n_ms; b += 32) {
-      const int q = P.ms_q[b];
-      const uint32_t hbit = (H >> q) & 1u;
-      const VecT* xn = u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)]);
-      const uint32_t n0 = P.ck1[p_low];                  // rows of this tile whose bit k-1 is clear (they come first)
-      if (hbit == 0) { ms_lo[g * nms + b] = n0; ms_len[g * nms + b] = size - n0; ms_ptr[g * nms + b] = xn - n0; }
-      else { ms_lo[g * nms + b] = 0; ms_len[g * nms + b] = n0; ms_ptr[g * nms + b] = xn + P.ck1[p_low + 1]; }
-      ms_amp[g * nms + b] = P.ms_amp[b];
-    }
-    if (lane == 0) {
-      s_cnt[2 * g] = n_ext;
-      s_cnt[2 * g + 1] = n_int;
-      s_dt[g] = P.tile_diag[H];
-      s_base[g] = (int64_t)P.tile_base[H];
-    }
-  }
-  if (P.diag_mode == 1) {
-    for (int i = tid; i < G * P.n_codes; i += THREADS) {
-      const int g = i / P.n_codes, code = i - g * P.n_codes;
-      const uint32_t H = (hi << gm) | P.gmid[c][g];
-      double v = P.dval[code];
-      if (P.mq_folded) {
-        const uint32_t pat = P.dpat[code];
-        for (int e = 0; e < P.n_mq; ++e)
-          if (((H >> P.mq_q[e]) & 1u) && ((pat >> P.mq_pidx[e]) & 1u)) v += P.mq_coef[e];
-      }
-      s_dval[i] = v;
-    }
-  }
-  for (int g = 0; g < G; ++g) {
-    const uint32_t H = (hi << gm) | P.gmid[c][g];
-    const VecT* xo = u1_seg_resolve<VecT>(P, P.tile_base[H]);   // shards are aligned to hi blocks: one segment per tile
-    VecT* xg = xs + g * xstride;
-    for (uint32_t i = tid; i < size; i += THREADS) xg[i] = ldg_val(xo + i);
-    if (tid == 0) xg[size] = vzero((VecT*)nullptr);
-  }
-  __syncthreads();
-
-  U1GView<VecT> V;
-  V.xs = xs; V.xstride = xstride; V.dval = s_dval; V.n_codes = P.n_codes;
-  V.hh_ptr = hh_ptr; V.hh_amp = hh_amp; V.int_amp = int_amp; V.int_src = int_src;
-  V.ms_ptr = ms_ptr; V.ms_amp = ms_amp; V.ms_lo = ms_lo; V.ms_len = ms_len;
-  V.mx_ptr = mx_ptr; V.mx_amp = mx_amp; V.mx_toff = mx_toff;
-  V.dt = s_dt; V.base = s_base; V.cnt = s_cnt;
-  V.nh = nh; V.nms = nms; V.nmx = nmx;
-  V.lofs = lofs; V.gofs = P.grpofs[p_low]; V.size = size; V.p_low = p_low;
-  double dre = 0.0, dim_ = 0.0;
-  const bool want_dot = dot_partials != nullptr;
-  switch (G) {
-    case 1: u1g_body<VecT, THREADS, 1, RS>(P, V, y, want_dot, dre, dim_); break;
-    case 2: u1g_body<VecT, THREADS, 2, RS>(P, V, y, want_dot, dre, dim_); break;
-    case 3: u1g_body<VecT, THREADS, 3, RS>(P, V, y, want_dot, dre, dim_); break;
-    case 4: u1g_body<VecT, THREADS, 4, RS>(P, V, y, want_dot, dre, dim_); break;
-    case 6: u1g_body<VecT, THREADS, 6, RS>(P, V, y, want_dot, dre, dim_); break;
-    default: break;
-  }
-  if (dot_partials) {
-    __shared__ double s_red[2][THREADS / 32];
-    dre = warp_sum(dre);
-    dim_ = warp_sum(dim_);
-    if ((tid & 31) == 0) { s_red[0][tid >> 5] = dre; s_red[1][tid >> 5] = dim_; }
-    __syncthreads();
-    if (tid == 0) {
-      double a = 0, cc = 0;
-      for (int w = 0; w < THREADS / 32; ++w) { a += s_red[0][w]; cc += s_red[1][w]; }
-      dot_partials[2 * blockIdx.x] = a;
-      dot_partials[2 * blockIdx.x + 1] = cc;
     }
   }
 }
@@ -949,21 +532,6 @@ uint64_t binom_u64(int n, int k) {
   return (uint64_t)r;
 }
 
-struct GroupCfg { bool on = false; int k = 14, m = 4, threads = 1024, rs = 2; };
-
-// EDCUDA_U1_G="k,m,threads,rows_per_pass" selects the group kernel; "0" forces the single-tile kernel
-GroupCfg group_cfg(int n_bits, int vec_bytes) {
-  GroupCfg g;
-  if (const char* e = getenv("EDCUDA_U1_G")) {
-    int k, m, t, r;
-    if (sscanf(e, "%d,%d,%d,%d", &k, &m, &t, &r) == 4 && k >= 2 && k <= 16 && m >= 0 && m <= 4 && k + m <= n_bits) {
-      g.on = true; g.k = k; g.m = m; g.threads = t; g.rs = r;
-    }
-  }
-  (void)vec_bytes;
-  return g;
-}
-
 int choose_k(int n_bits, int vec_bytes) {
   int k = std::min(15, std::max(4, n_bits - 10));   // k = 15 measured best on B200 (L=32: k=14 11.4 ms, k=15 9.1 ms, k=16 12.2 ms)
   k = std::min(k, n_bits);
@@ -978,7 +546,7 @@ int choose_k(int n_bits, int vec_bytes) {
 
 }  // namespace
 
-static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes, bool allow_group = true) {
+static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   auto plan = std::make_shared<FastU1Plan>();
   ed_basis* b = o->basis;
   plan->vec_bytes = vec_bytes;
@@ -987,9 +555,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes, bool a
   if (n_bits < 1 || n_bits > 42) return plan;
   Lowered L = lower_operator(o->op, n_bits, n_set);
   if (!L.ok) return plan;
-  GroupCfg gcfg = group_cfg(n_bits, vec_bytes);
-  if (!allow_group) gcfg.on = false;
-  const int k = gcfg.on ? gcfg.k : choose_k(n_bits, vec_bytes);
+  const int k = choose_k(n_bits, vec_bytes);
   const int hb = n_bits - k;
   if (hb > 26) return plan;  // tile tables of 2^hb entries
   U1Params& P = plan->P;
@@ -1121,55 +687,6 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes, bool a
     }
     if (ll) lls.push_back({c.d, (uint32_t)(ll & lowmask), c.v});
   }
-  // nearest-neighbour low bonds go to the delta LUTs (needs bit 7 inside the low word); the ELL keeps the rest
-  P.lut_on = 0;
-  for (int j = 0; j < 16; ++j) P.nn_amp[j] = 0.0;
-  uint32_t nn_mask = 0;
-  if (k >= 8 && !gcfg.on && !getenv("EDCUDA_U1_NOLUT")) {
-    std::vector<LL> rest;
-    for (auto& l : lls) {
-      if (l.d != 1) { rest.push_back(l); continue; }
-      for (int p = 0; p + 1 < k; ++p)
-        if (l.mask >> p & 1u) { P.nn_amp[p] += l.amp; nn_mask |= 1u << p; }
-    }
-    if (nn_mask) { P.lut_on = 1; lls.swap(rest); }
-  }
-  if (P.lut_on) {
-    std::vector<uint64_t> lut_lo(256, 0);
-    for (uint32_t b = 0; b < 256; ++b) {
-      uint64_t e = 0;
-      for (int j = 0; j < 7; ++j) {
-        if (!(nn_mask >> j & 1u) || ((b >> j) & 1u) == ((b >> (j + 1)) & 1u)) continue;
-        const int r = __builtin_popcount(b & ((1u << j) - 1u));
-        const int64_t dlt = (int64_t)binom_u64(j, r);
-        const int8_t sd = (int8_t)(((b >> j) & 1u) ? dlt : -dlt);      // particle on j moves up: the word (and its rank) grows
-        e |= (uint64_t)(uint8_t)sd << (8 * j);
-      }
-      lut_lo[b] = e;
-    }
-    const uint32_t nu = 1u << (k - 7);
-    std::vector<uint4> lut_up((size_t)(k + 1) * nu, make_uint4(0, 0, 0, 0));
-    for (int p = 0; p <= k; ++p)
-      for (uint32_t u = 0; u < nu; ++u) {
-        uint16_t ent[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < 8; ++j) {
-          const int q = 7 + j;
-          if (q + 1 >= k || !(nn_mask >> q & 1u)) continue;
-          const uint32_t bq = (u >> j) & 1u, bq1 = (u >> (j + 1)) & 1u;
-          if (bq == bq1) continue;
-          const int r = p - __builtin_popcount(u >> j);               // set bits below q
-          if (r < 0 || r > q) continue;                               // word not in this popcount class
-          const int64_t dlt = (int64_t)binom_u64(q, r);
-          ent[j] = (uint16_t)(int16_t)(bq ? dlt : -dlt);
-        }
-        lut_up[(size_t)p * nu + u] = make_uint4(ent[0] | ((uint32_t)ent[1] << 16), ent[2] | ((uint32_t)ent[3] << 16),
-                                                ent[4] | ((uint32_t)ent[5] << 16), ent[6] | ((uint32_t)ent[7] << 16));
-      }
-    plan->lut_lo.upload(lut_lo);
-    plan->lut_up.upload(lut_up);
-    P.lut_lo = plan->lut_lo.p;
-    P.lut_up = plan->lut_up.p;
-  }
   // classes with the same amplitude share one ELL table
   std::map<double, std::vector<LL>> by_amp;
   for (auto& l : lls) by_amp[l.amp].push_back(l);
@@ -1272,49 +789,6 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes, bool a
     }
   }
 
-  // ---- groups (k2_apply_u1g): every (hi, popcount(mid)) class with a valid low popcount --------------------------
-  P.gm = 0; P.gcap = 1; P.n_codes = 1; P.grp = nullptr; P.grp_first = 0;
-  if (P.diag_mode == 1) { int mc = 0; for (uint8_t cde : dcode) mc = std::max(mc, (int)cde); P.n_codes = mc + 1; }
-  if (gcfg.on && P.diag_mode != 2 && (P.n_mq == 0 || P.mq_folded) && gcfg.m <= hb) {
-    const int gm = gcfg.m;
-    P.gm = gm;
-    memset(P.gcount, 0, sizeof(P.gcount));
-    memset(P.gmid, 0, sizeof(P.gmid));
-    for (uint32_t mid = 0; mid < (1u << gm); ++mid) {
-      const int cc = __builtin_popcount(mid);
-      P.gmid[cc][P.gcount[cc]++] = (uint8_t)mid;
-    }
-    for (int cc = 0; cc <= gm; ++cc) P.gcap = std::max<int>(P.gcap, P.gcount[cc]);
-    std::vector<uint32_t> grp;
-    for (uint32_t hi = 0; hi < (nH >> gm); ++hi) {
-      bool any = false;
-      for (int cc = 0; cc <= gm; ++cc) {
-        const int p_low = n_set - __builtin_popcount(hi) - cc;
-        if (p_low < 0 || p_low > k) continue;
-        grp.push_back((hi << 3) | (uint32_t)cc);
-        uint64_t lo = ~0ull, hiend = 0;
-        for (int g = 0; g < P.gcount[cc]; ++g) {
-          const uint32_t H = (hi << gm) | P.gmid[cc][g];
-          lo = std::min(lo, tile_base[H]);
-          hiend = std::max(hiend, tile_base[H] + binom_u64(k, p_low));
-        }
-        plan->g_lo.push_back(lo);
-        plan->g_hi.push_back(hiend);
-        if (!any) { plan->blk_base.push_back(lo); any = true; }
-        else plan->blk_base.back() = std::min(plan->blk_base.back(), lo);
-      }
-    }
-    const U1GLayout GL = u1g_layout(P.gcap, tile_cap, vec_bytes, P.n_codes, std::max(P.n_hh, 1), std::max(P.n_ms, 1), std::max(P.n_mx, 1));
-    if (!grp.empty() && GL.total <= 227 * 1024) {
-      plan->grp.upload(grp);
-      P.grp = plan->grp.p;
-      plan->g_on = true;
-      plan->g_threads = gcfg.threads;
-      plan->g_rs = gcfg.rs;
-      plan->g_smem = GL.total;
-    }
-  }
-
   auto nonempty8 = [](std::vector<uint8_t>& v) { if (v.empty()) v.push_back(0); };
   auto nonemptyd = [](std::vector<double>& v) { if (v.empty()) v.push_back(0.0); };
   nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q); nonempty8(ms_q); nonempty8(mq_pidx);
@@ -1339,14 +813,9 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes, bool a
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
   P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
   P.ms_q = plan->ms_q.p; P.ms_amp = plan->ms_amp.p;
-  P.cap_hh = std::max(P.n_hh, 1); P.cap_mx = std::max(P.n_mx, 1); P.cap_ms = std::max(P.n_ms, 1);
-  P.cap_mq = P.mq_folded ? 1 : std::max(P.n_mq, 1);
-  P.cap_codes = P.diag_mode == 1 ? P.n_codes : 1;
-  plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (size_t)(P.cap_hh + P.cap_mx + P.cap_mq + P.cap_codes) * 8 +
-                     (size_t)(P.cap_hh + P.cap_mx) * 8 + (size_t)P.cap_ms * 16 + (size_t)(P.cap_mx + P.cap_mq + 2 * P.cap_ms) * 4;
-  if (P.lut_on) plan->smem_bytes += 16 + ((size_t)16 << (k - 7)) + 256 * 8;
+  plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
+                     (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4 + U1_MAX_MS * (4 + 4 + 8 + 8);
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
-  if (gcfg.on && !plan->g_on) return build_plan(o, vec_bytes, false);   // group layout does not fit: single-tile kernel, its own k
   plan->supported = true;
   return plan;
 }
@@ -1379,32 +848,6 @@ static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, void* o
   ED_LAUNCH(kern, n_launch, U1_THREADS, plan->smem_bytes, P, reinterpret_cast<VecT*>(out), partials);
 }
 
-template <typename VecT, int THREADS, int RS, int MINB>
-static void launch_u1g_inst(FastU1Plan* plan, const U1Params& P, int n_launch, void* out, double* partials) {
-  auto kern = k2_apply_u1g<VecT, THREADS, RS, MINB>;
-  static thread_local size_t configured = 0;
-  if (plan->g_smem > 48 * 1024 && configured < plan->g_smem) {
-    ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->g_smem));
-    configured = plan->g_smem;
-  }
-  ED_LAUNCH(kern, n_launch, THREADS, plan->g_smem, P, reinterpret_cast<VecT*>(out), partials);
-}
-
-template <typename VecT>
-static void launch_u1g(FastU1Plan* plan, const U1Params& P, int n_launch, void* out, double* partials) {
-  const bool two = plan->g_smem <= 112 * 1024;     // two CTAs per SM fit
-  const int t = plan->g_threads, r = plan->g_rs;
-  if (t == 1024 && r == 2) launch_u1g_inst<VecT, 1024, 2, 1>(plan, P, n_launch, out, partials);
-  else if (t == 896 && r == 2) launch_u1g_inst<VecT, 896, 2, 1>(plan, P, n_launch, out, partials);
-  else if (t == 768 && r == 2) launch_u1g_inst<VecT, 768, 2, 1>(plan, P, n_launch, out, partials);
-  else if (t == 512 && r == 4 && !two) launch_u1g_inst<VecT, 512, 4, 1>(plan, P, n_launch, out, partials);
-  else if (t == 512 && r == 4) launch_u1g_inst<VecT, 512, 4, 2>(plan, P, n_launch, out, partials);
-  else if (t == 512 && r == 2 && two) launch_u1g_inst<VecT, 512, 2, 2>(plan, P, n_launch, out, partials);
-  else if (t == 448 && r == 2 && two) launch_u1g_inst<VecT, 448, 2, 2>(plan, P, n_launch, out, partials);
-  else if (t == 448 && r == 4 && two) launch_u1g_inst<VecT, 448, 4, 2>(plan, P, n_launch, out, partials);
-  else ED_REQUIRE(false, ED_ERR_ARGUMENT, "EDCUDA_U1_G: no kernel instance for this (threads, rows per pass, shared memory) combination");
-}
-
 // contiguous, count-balanced row ranges whose boundaries fall on tile boundaries (so every tile, and therefore every
 // neighbour stream, lives in exactly one x segment)
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi) {
@@ -1414,10 +857,9 @@ void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo
     if (target <= 0) return 0;
     if (target >= dim) return dim;
     if (!plan->supported) return target;
-    const std::vector<uint64_t>& bases = plan->g_on ? plan->blk_base : plan->h_base;
-    auto it = std::lower_bound(bases.begin(), bases.end(), (uint64_t)target);
-    int64_t up = it == bases.end() ? dim : (int64_t)*it;
-    int64_t down = it == bases.begin() ? 0 : (int64_t)*(it - 1);
+    auto it = std::lower_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)target);
+    int64_t up = it == plan->h_base.end() ? dim : (int64_t)*it;
+    int64_t down = it == plan->h_base.begin() ? 0 : (int64_t)*(it - 1);
     return (up - target <= target - down) ? up : down;
   };
   *lo = snap(dim / world * rank + std::min<int64_t>(rank, dim % world));
@@ -1452,39 +894,10 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
       P.seg_ptr[s] = o->x_seg_ptr[s];
       if (s > 0) {
         const uint64_t b = (uint64_t)o->x_seg_lo[s];
-        const std::vector<uint64_t>& bases = plan->g_on ? plan->blk_base : plan->h_base;
-        ED_REQUIRE(b == (uint64_t)o->dim || std::binary_search(bases.begin(), bases.end(), b), ED_ERR_ARGUMENT,
+        ED_REQUIRE(b == (uint64_t)o->dim || std::binary_search(plan->h_base.begin(), plan->h_base.end(), b), ED_ERR_ARGUMENT,
                    "x segment boundaries must fall on tile boundaries (use ed_oprep_suggest_rows)");
       }
     }
-  }
-  if (plan->g_on) {
-    // groups overlapping the owned rows (a group's tiles interleave with other groups of its hi block)
-    static thread_local FastU1Plan* c_plan = nullptr;
-    static thread_local int64_t c_lo = -1, c_hi = -1;
-    static thread_local int c_first = 0, c_n = 0;
-    if (c_plan != plan || c_lo != o->row_lo || c_hi != o->row_hi) {
-      int gf = -1, gl = -1;
-      for (size_t g = 0; g < plan->g_lo.size(); ++g)
-        if ((int64_t)plan->g_hi[g] > o->row_lo && (int64_t)plan->g_lo[g] < o->row_hi) { if (gf < 0) gf = (int)g; gl = (int)g; }
-      c_plan = plan; c_lo = o->row_lo; c_hi = o->row_hi;
-      c_first = std::max(gf, 0); c_n = gf < 0 ? 0 : gl - gf + 1;
-    }
-    P.grp_first = c_first;
-    const int n_launch = c_n;
-    if (n_launch <= 0 || o->row_hi <= o->row_lo) {
-      if (alpha_dot) ED_CUDA(cudaMemsetAsync(alpha_dot, 0, 2 * sizeof(double), ed_stream()));
-      return;
-    }
-    double* partials = nullptr;
-    if (alpha_dot) {
-      if (plan->partials.n < (size_t)2 * plan->g_lo.size()) plan->partials.alloc((size_t)2 * plan->g_lo.size());
-      partials = plan->partials.p;
-    }
-    if (dtype == ED_F64) launch_u1g<double>(plan, P, n_launch, out, partials);
-    else launch_u1g<c128>(plan, P, n_launch, out, partials);
-    if (alpha_dot) ed_reduce_pairs(partials, n_launch, alpha_dot);
-    return;
   }
   // tiles overlapping the owned rows [row_lo, row_hi)
   int first = (int)(std::upper_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)std::max<int64_t>(o->row_lo, 0)) - plan->h_base.begin()) - 1;
@@ -1506,8 +919,6 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   static const int r_f64 = getenv("EDCUDA_U1_R") ? atoi(getenv("EDCUDA_U1_R")) : 7;
   if (dtype == ED_F64 && r_f64 == 7) launch_u1<double, 7>(plan, P, n_launch, out, partials);
   else if (dtype == ED_F64 && r_f64 == 5) launch_u1<double, 5>(plan, P, n_launch, out, partials);
-  else if (dtype == ED_F64 && r_f64 == 4) launch_u1<double, 4>(plan, P, n_launch, out, partials);
-  else if (dtype == ED_F64 && r_f64 == 6) launch_u1<double, 6>(plan, P, n_launch, out, partials);
   else if (dtype == ED_F64) launch_u1<double, 13>(plan, P, n_launch, out, partials);
   else launch_u1<c128, 7>(plan, P, n_launch, out, partials);
   if (alpha_dot) ed_reduce_pairs(partials, n_launch, alpha_dot);

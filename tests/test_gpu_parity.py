@@ -757,59 +757,27 @@ def test_fast_path_vs_c_oracle(gpu_ed, n, n_dn, model):
     assert rel_err(np.concatenate(parts), exp) < TOL
 
 
-@pytest.mark.parametrize("n,n_dn,model,gcfg", [(20, 10, "xxz", "8,4,1024,2"), (20, 10, "xxz", "7,3,512,4"), (20, 7, "j1j2_field", "6,3,512,2"),
-                                               (16, 8, "square", "5,2,448,2"), (16, 5, "triangular", "6,4,896,2"),
-                                               (22, 11, "xxz", "9,1,768,2"), (18, 9, "j1j2_field", "6,0,448,4"),
-                                               (24, 12, "xxz", "12,4,1024,2")])
-def test_group_kernel_vs_c_oracle(gpu_ed, n, n_dn, model, gcfg, monkeypatch):
-    """k2_apply_u1g (one CTA = all tiles of a (high bits, mid popcount) class; EDCUDA_U1_G = k,m,threads,rows per pass)
-    against the oracle's C twin: matvec, accumulate, complex vectors, <x,Hx> epilogue, arbitrary row shards and
-    x handed over as block-aligned segments (the multi-GPU input form, here three buffers on one device)."""
+@pytest.mark.parametrize("n,n_dn,model", [(20, 10, "xxz"), (20, 7, "j1j2"), (22, 11, "xxz")])
+def test_fast_path_segmented_input_single_gpu(gpu_ed, n, n_dn, model):
+    """The multi-GPU input form on one device: x handed over as three tile-aligned segments in separate buffers
+    (ed_oprep_suggest_rows + ed_oprep_set_x_segments), every "rank" applying its rows with the fused <x,Hx> epilogue."""
     ed = gpu_ed
     import ctypes as C
     import torch
     from edcuda._lib import lib, check
-    monkeypatch.setenv("EDCUDA_U1_G", gcfg)
-    L = ed.lattices
-    hs, pauli = ed.spin_half_system(n)
+    hs, _ = ed.spin_half_system(n)
     if model == "xxz":
-        h = ed.models.xxz_bonds(hs, L.chain_bonds(n), 1.0, 0.37)
-    elif model == "j1j2_field":
-        h = ed.simplify(ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 1)) + ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 2), 0.5)
-                        + sum(0.3 * pauli(i, "z") for i in range(0, n, 2)) + 1.25 * ed.Operator([(0, 0, 0, 1.0)]))
-    elif model == "square":
-        h = ed.models.heisenberg_bonds(hs, L.square_bonds(4, 4))
+        h = ed.models.xxz_bonds(hs, ed.lattices.chain_bonds(n), 1.0, 0.37)
     else:
-        h = ed.models.heisenberg_bonds(hs, L.triangular_bonds(4, 4), 0.25)
+        h = ed.simplify(ed.models.heisenberg_bonds(hs, ed.lattices.chain_bonds(n, 1)) + ed.models.heisenberg_bonds(hs, ed.lattices.chain_bonds(n, 2), 0.5))
     hsr = ed.represent(ed.HilbertSpaceSector(hs, n - 2 * n_dn))
     d = hsr.dimension
-    rng = np.random.default_rng(n + n_dn)
-    x = rng.standard_normal(d)
+    x = np.random.default_rng(n).standard_normal(d)
     _, exp = _c_oracle_apply(n, n_dn, h, x)
-    fast = ed.represent(hsr, h)
-    y = np.zeros(d)
-    ed.mul_b(y, fast, x)
-    assert rel_err(y, exp) < TOL
-    ed.apply_b(y, x, fast)
-    assert rel_err(y, 2 * exp) < TOL
-    xc = x + 1j * rng.standard_normal(d)
-    _, expc = _c_oracle_apply(n, n_dn, h, xc)
-    yc = np.zeros(d, dtype=complex)
-    ed.mul_b(yc, fast, xc)
-    assert rel_err(yc, expc) < TOL
-    # arbitrary row shards (groups straddling a shard boundary mask their stores)
-    cuts = [0, d // 7, d // 2 + 3, d]
-    parts = []
-    for lo, hi in zip(cuts[:-1], cuts[1:]):
-        out = np.zeros(hi - lo)
-        ed.mul_b(out, ed.represent(hsr, h).set_rows(lo, hi), x)
-        parts.append(out)
-    assert rel_err(np.concatenate(parts), exp) < TOL
-    # segmented x: three "ranks" on one device, shard boundaries suggested by the library, fused <x,Hx>
     world = 3
     xt = torch.from_numpy(x).cuda()
-    ranges = []
     opr = ed.represent(hsr, h)
+    ranges = []
     for r in range(world):
         lo, hi = C.c_int64(), C.c_int64()
         check(lib.ed_oprep_suggest_rows(opr._handle, ed.ED_F64, world, r, C.byref(lo), C.byref(hi)))
@@ -819,7 +787,7 @@ def test_group_kernel_vs_c_oracle(gpu_ed, n, n_dn, model, gcfg, monkeypatch):
     seg_lo = (C.c_int64 * (world + 1))(*([r[0] for r in ranges] + [d]))
     ptrs = (C.c_void_p * world)(*[t.data_ptr() for t in segs])
     outs, dots = [], []
-    for r, (lo, hi) in enumerate(ranges):
+    for lo, hi in ranges:
         o_r = ed.represent(hsr, h).set_rows(lo, hi)
         check(lib.ed_oprep_set_x_segments(o_r._handle, world, seg_lo, ptrs))
         y_r = torch.zeros(hi - lo, dtype=torch.float64, device="cuda")

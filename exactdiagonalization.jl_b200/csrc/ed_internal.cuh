@@ -217,6 +217,13 @@ struct SymDev {
   DevBuf<double> chi;      // [n_ops][2]
   DevBuf<int32_t> inverse; // [n_ops]
   DevBuf<uint8_t> chi_is_one;  // [n_ops]  |chi-1| <= tol
+  // Translation factorisation (1-bit sites, site = x + tr_n1 * y): when the group contains the n1 x n2 lattice
+  // translations T, G is swept as cosets T p_j -- p_j through its 6-bit LUT, the translations as rotate-within-field /
+  // rotate-word ALU steps (reduced_staged.cu: k6b_canonicalize_tr).
+  bool tr_on = false;
+  int tr_n1 = 0, tr_n2 = 0, tr_ncos = 0;
+  DevBuf<uint64_t> tr_lut6;    // [(j*n_chunks6 + c)*64 + v] for the coset representatives p_j
+  DevBuf<int32_t> tr_inv;      // [(j*n2 + b)*n1 + a] = inverse index of the element Tx^a Ty^b p_j
 };
 
 struct SymDesc {

@@ -116,6 +116,96 @@ k6b_canonicalize(int n_ops, const uint64_t* __restrict__ lut6, const int32_t* __
   }
 }
 
+// B (translation-factorised): the same minimum / element selection as k6b_canonicalize, but the group is swept as
+// cosets T p_j of the lattice translations T = {Tx^a Ty^b}: one 6-bit-LUT image per coset representative p_j, then
+// the n1 x n2 translations as ALU steps on the image (Tx = rotate every n1-bit field by one, Ty = rotate the word by
+// n1).  |G| / (n1 n2) LUT images per word instead of |G|: the sweep moves from the shared-memory pipe (bank
+// conflicts of the LUT gathers) to the integer pipes.  tinv[(j*n2 + b)*n1 + a] = inverse index of Tx^a Ty^b p_j.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+k6b_canonicalize_tr(int n_cos, int n1, int n2, int n_bits, const uint64_t* __restrict__ lut6c, const int32_t* __restrict__ tinv,
+                    int64_t n_words, uint64_t* __restrict__ words, uint16_t* __restrict__ garg) {
+  constexpr int W = 4;          // words per thread
+  constexpr int CB = 4;         // cosets staged per barrier
+  extern __shared__ __align__(16) unsigned char k6_smem[];
+  uint64_t* s_lut = reinterpret_cast<uint64_t*>(k6_smem);                   // [2][CB * NCH * 64]
+  int32_t* s_inv = reinterpret_cast<int32_t*>(s_lut + 2 * CB * NCH * 64);   // [2][CB * n1 * n2]
+  const int nt = n1 * n2;
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)blockIdx.x * (256 * W);
+  const uint64_t full = n_bits >= 64 ? ~0ull : ((1ull << n_bits) - 1ull);
+  uint64_t m_lo = 0;
+  for (int y = 0; y < n2; ++y) m_lo |= 1ull << (n1 * y);
+  const uint64_t m_hi = full & ~m_lo;
+  uint64_t w[W], best[W];
+  int besti[W];
+  uint32_t off[W][NCH];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int64_t i = base + tid + k * 256;
+    w[k] = i < n_words ? words[i] : 0ull;
+    best[k] = w[k];
+    besti[k] = 0;   // identity (element 0, its own inverse)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) off[k][c] = (uint32_t)((w[k] >> (6 * c)) & 63ull) + c * 64;
+  }
+  const int n_batches = (n_cos + CB - 1) / CB;
+  auto stage = [&](int batch, int buf) {
+    const int j0 = batch * CB;
+    const int nj = min(CB, n_cos - j0);
+    const uint64_t* src = lut6c + (size_t)j0 * NCH * 64;
+    uint64_t* dst = s_lut + (size_t)buf * CB * NCH * 64;
+    for (int i = tid; i < nj * NCH * 64; i += 256) dst[i] = __ldg(src + i);
+    int32_t* di = s_inv + (size_t)buf * CB * nt;
+    for (int i = tid; i < nj * nt; i += 256) di[i] = __ldg(tinv + (size_t)j0 * nt + i);
+  };
+  stage(0, 0);
+  __syncthreads();
+  for (int batch = 0; batch < n_batches; ++batch) {
+    const int buf = batch & 1;
+    if (batch + 1 < n_batches) stage(batch + 1, buf ^ 1);
+    const int nj = min(CB, n_cos - batch * CB);
+    for (int ji = 0; ji < nj; ++ji) {
+      const uint64_t* L = s_lut + ((size_t)buf * CB + ji) * NCH * 64;
+      const int32_t* inv_tab = s_inv + ((size_t)buf * CB + ji) * nt;
+      uint64_t im[W];
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) v |= L[off[k][c]];
+        im[k] = v;
+      }
+#pragma unroll 1
+      for (int b = 0; b < n2; ++b) {
+        uint64_t u[W];
+#pragma unroll
+        for (int k = 0; k < W; ++k) u[k] = im[k];
+#pragma unroll 1
+        for (int a = 0; a < n1; ++a) {
+#pragma unroll
+          for (int k = 0; k < W; ++k) {
+            if (u[k] <= best[k]) {                       // rare after the first few elements
+              const int inv = inv_tab[b * n1 + a];
+              if (u[k] < best[k]) { best[k] = u[k]; besti[k] = inv; }
+              else if (inv > besti[k]) besti[k] = inv;
+            }
+            u[k] = ((u[k] << 1) & m_hi) | ((u[k] >> (n1 - 1)) & m_lo);          // Tx
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < W; ++k) im[k] = ((im[k] << n1) | (im[k] >> (n_bits - n1))) & full;   // Ty
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int64_t i = base + tid + k * 256;
+    if (i < n_words) { words[i] = best[k]; garg[i] = (uint16_t)besti[k]; }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int64_t n, int64_t out_row0,
             const int64_t* __restrict__ offs, const uint64_t* __restrict__ min_words, const uint16_t* __restrict__ garg,
@@ -239,7 +329,15 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
       const int nch = rb->symdev.n_chunks6;
       const uint64_t* lut6 = rb->symdev.lut6.p;
       const int32_t* inv = rb->symdev.inverse.p;
-      if (nch <= 4) ED_LAUNCH(k6b_canonicalize<4>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+      const SymDev& sd = rb->symdev;
+      if (sd.tr_on && nch <= 8) {
+        const size_t smem = (size_t)2 * 4 * nch * 64 * 8 + (size_t)2 * 4 * sd.tr_n1 * sd.tr_n2 * 4;
+        const int nb_ = parent->space.bits;
+        if (nch <= 4) ED_LAUNCH(k6b_canonicalize_tr<4>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+        else if (nch <= 6) ED_LAUNCH(k6b_canonicalize_tr<6>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+        else ED_LAUNCH(k6b_canonicalize_tr<8>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+      }
+      else if (nch <= 4) ED_LAUNCH(k6b_canonicalize<4>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
       else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
       else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
       else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);

@@ -111,6 +111,63 @@ void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, 
     }
     flipmask[g] = sym.flip[g] ? space.fullmask() : 0ull;
   }
+  // ---- translation factorisation: G = union of cosets T p_j with T the n1 x n2 lattice translations ------------------
+  out->tr_on = false;
+  if (sym.is_group && space.bits == n && n >= 4 && n <= 60 && G >= 8 && !getenv("EDCUDA_K6_NOTR")) {
+    std::map<std::vector<int32_t>, int> index;
+    std::vector<int32_t> key(n + 1);
+    for (int g = 0; g < G; ++g) {
+      for (int i = 0; i < n; ++i) key[i] = sym.perm[(size_t)g * n + i];
+      key[n] = sym.flip[g];
+      index.emplace(key, g);
+    }
+    auto tmap = [&](int n1, int n2, int a, int b, int i) { const int x = i % n1, y = i / n1; return (x + a) % n1 + n1 * ((y + b) % n2); };
+    int best_n1 = 0;
+    for (int n1 = n; n1 >= 2 && !best_n1; --n1) {
+      if (n % n1) continue;
+      const int n2 = n / n1;
+      bool ok = true;
+      for (int gen = 0; gen < 2 && ok; ++gen) {
+        if (gen == 1 && n2 == 1) break;
+        for (int i = 0; i < n; ++i) key[i] = tmap(n1, n2, gen == 0 ? 1 : 0, gen == 1 ? 1 : 0, i);
+        key[n] = 0;
+        ok = index.count(key) != 0;
+      }
+      if (ok) best_n1 = n1;
+    }
+    if (best_n1 && G % n == 0) {
+      const int n1 = best_n1, n2 = n / n1, nt = n, ncos = G / nt;
+      std::vector<int> coset_of(G, -1);
+      std::vector<int> reps;
+      std::vector<int32_t> tinv((size_t)ncos * nt, 0);
+      bool ok = true;
+      for (int g = 0; g < G && ok; ++g) {
+        if (coset_of[g] >= 0) continue;
+        const int j = (int)reps.size();
+        if (j >= ncos) { ok = false; break; }
+        reps.push_back(g);
+        for (int b = 0; b < n2 && ok; ++b)
+          for (int a = 0; a < n1 && ok; ++a) {
+            for (int i = 0; i < n; ++i) key[i] = tmap(n1, n2, a, b, sym.perm[(size_t)g * n + i]);   // (t p)(i) = t.map[p.map[i]]
+            key[n] = sym.flip[g];
+            auto it = index.find(key);
+            if (it == index.end() || coset_of[it->second] >= 0) { ok = false; break; }
+            coset_of[it->second] = j;
+            tinv[((size_t)j * n2 + b) * n1 + a] = sym.inverse[it->second];
+          }
+      }
+      if (ok && (int)reps.size() == ncos) {
+        std::vector<uint64_t> tl((size_t)ncos * n_chunks6 * 64);
+        for (int j = 0; j < ncos; ++j)
+          std::copy(lut6.begin() + (size_t)reps[j] * n_chunks6 * 64, lut6.begin() + (size_t)(reps[j] + 1) * n_chunks6 * 64,
+                    tl.begin() + (size_t)j * n_chunks6 * 64);
+        out->tr_lut6.upload(tl);
+        out->tr_inv.upload(tinv);
+        out->tr_on = true;
+        out->tr_n1 = n1; out->tr_n2 = n2; out->tr_ncos = ncos;
+      }
+    }
+  }
   out->tgt_bit.upload(tgt_bit);
   out->flipmask.upload(flipmask);
   out->n_chunks6 = n_chunks6;

@@ -183,15 +183,19 @@ k6b_canonicalize_tr(int n_cos, int n1, int n2, int n_bits, const uint64_t* __res
         for (int k = 0; k < W; ++k) u[k] = im[k];
 #pragma unroll 1
         for (int a = 0; a < n1; ++a) {
+          bool hit = false;
 #pragma unroll
-          for (int k = 0; k < W; ++k) {
-            if (u[k] <= best[k]) {                       // rare after the first few elements
-              const int inv = inv_tab[b * n1 + a];
+          for (int k = 0; k < W; ++k) hit |= u[k] <= best[k];
+          if (__any_sync(0xffffffffu, hit)) {            // a real (warp-uniform) branch: new minima and ties are rare
+            const int inv = inv_tab[b * n1 + a];
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
               if (u[k] < best[k]) { best[k] = u[k]; besti[k] = inv; }
-              else if (inv > besti[k]) besti[k] = inv;
+              else if (u[k] == best[k] && inv > besti[k]) besti[k] = inv;
             }
-            u[k] = ((u[k] << 1) & m_hi) | ((u[k] >> (n1 - 1)) & m_lo);          // Tx
           }
+#pragma unroll
+          for (int k = 0; k < W; ++k) u[k] = ((u[k] << 1) & m_hi) | ((u[k] >> (n1 - 1)) & m_lo);          // Tx
         }
 #pragma unroll
         for (int k = 0; k < W; ++k) im[k] = ((im[k] << n1) | (im[k] >> (n_bits - n1))) & full;   // Ty
@@ -304,7 +308,13 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
   const int grid_c_max = sm * 16;
   if (alpha_dot && sc.partials.n < (size_t)2 * grid_c_max * n_batches) sc.partials.alloc((size_t)2 * grid_c_max * n_batches);
   int slots_used = 0;
+  // EDCUDA_K6_TIMING=1: per-phase device times of this call on stderr (profiling aid; adds event records only)
+  static const bool timing = getenv("EDCUDA_K6_TIMING") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float t_phase[3] = {0.f, 0.f, 0.f};
+  if (timing) for (auto& e : ev) ED_CUDA(cudaEventCreate(&e));
   for (int64_t b0 = 0; b0 < n_rows; b0 += batch_rows) {
+    if (timing) ED_CUDA(cudaEventRecord(ev[0], ed_stream()));
     const int64_t nb = std::min(batch_rows, n_rows - b0);
     const int64_t row0 = o->row_lo + b0;
     if (sc.counts.n < (size_t)nb + 1) { sc.counts.alloc((size_t)nb + 1); sc.offs.alloc((size_t)nb + 1); }
@@ -325,6 +335,7 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
     }
     if (n_hits > 0) {
       ED_LAUNCH(k6a_emit, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.offs.p, sc.words.p);
+      if (timing) ED_CUDA(cudaEventRecord(ev[1], ed_stream()));
       const int grid_b = (int)((n_hits + 1023) / 1024);
       const int nch = rb->symdev.n_chunks6;
       const uint64_t* lut6 = rb->symdev.lut6.p;
@@ -342,11 +353,21 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
       else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
       else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
     }
+    if (timing) ED_CUDA(cudaEventRecord(ev[2], ed_stream()));
     const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 127) / 128, (int64_t)grid_c_max));
     ED_LAUNCH(k6c_combine, grid_c, 128, 0, T, L, S, R, row0, nb, b0, sc.offs.p, sc.words.p, sc.garg.p,
               side == ED_SIDE_RIGHT ? 1 : 0, reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate,
               alpha_dot ? sc.partials.p : nullptr, slots_used);
     slots_used += grid_c;
+    if (timing && n_hits > 0) {
+      ED_CUDA(cudaEventRecord(ev[3], ed_stream()));
+      ED_CUDA(cudaEventSynchronize(ev[3]));
+      for (int q = 0; q < 3; ++q) { float ms = 0; ED_CUDA(cudaEventElapsedTime(&ms, ev[q], ev[q + 1])); t_phase[q] += ms; }
+    }
+  }
+  if (timing) {
+    fprintf(stderr, "[edcuda] K6 staged: emit %.2f ms, canonicalize %.2f ms, combine %.2f ms (%d batches)\n", t_phase[0], t_phase[1], t_phase[2], n_batches);
+    for (auto& e : ev) cudaEventDestroy(e);
   }
   if (alpha_dot) ed_reduce_pairs(sc.partials.p, slots_used, alpha_dot);
 }

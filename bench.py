@@ -271,6 +271,12 @@ def main():
     name = args.workload
     w = WORKLOADS[name]
     if args.impl == "reference":
+        if w["kind"] == "tri":
+            # the reference keeps 32 B per PARENT state (9.08e9 states -> 290 GB of maps): not runnable on this host,
+            # and the oracle's C twin only restates the plain-basis apply_parallel!
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "reference algorithm needs ~360 GB of host memory for the 6x6 triangular parent space (SURVEY 8d); no CPU arm for this workload"}))
+            return
         run_reference(args, w, name)
         return
 

@@ -309,6 +309,7 @@ void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accum
                       double* alpha_dot);
 bool ed_apply_reduced_linear_supported(ed_oprep* o);                                            // reduced_linear.cu
 void ed_apply_reduced_linear(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);
+bool ed_reduced_fill_raw_staged(ed_oprep* o, int side, int64_t line0, int64_t n, const int64_t* raw_offs, int64_t* raw_row, void* raw_val);  // reduced_staged.cu
 bool ed_apply_reduced_staged_supported(ed_oprep* o);                                            // reduced_staged.cu
 void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);                                                       // reduced.cu (K6)
 void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot);

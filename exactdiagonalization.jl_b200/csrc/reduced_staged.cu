@@ -266,6 +266,52 @@ k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int
   }
 }
 
+// sparse()/cached-CSR assembly for a reduced representation: the raw (index, amplitude) entries of k4_fill_raw
+// (sparse.cu: every matching term in term order, -1 for misses) with the orbit minima taken from the staged sweep
+// instead of one row-per-thread orbit search per hit.  Same arithmetic as k6c_combine / walk_line.
+__global__ void __launch_bounds__(128)
+k6c_fill_raw(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int64_t n, const int64_t* __restrict__ hit_offs,
+             const uint64_t* __restrict__ min_words, const uint16_t* __restrict__ garg, int conj_side,
+             const int64_t* __restrict__ raw_offs, int64_t* __restrict__ raw_row, c128* __restrict__ raw_val) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = row0 + i;
+    const uint64_t b = __ldg(R.words + r);
+    c128 a_self = reduced_rep_amp(S, R, r);
+    if (conj_side) a_self = cconj(a_self);
+    const c128 inv_self = cinv(a_self);
+    int64_t at = hit_offs[i];
+    int64_t out = raw_offs[i];
+    for (int t = 0; t < T.n_terms; ++t) {
+      const uint64_t m = __ldg(T.mask + t);
+      if ((b & m) != __ldg(T.match + t)) continue;
+      const uint64_t b2 = (b & ~m) | __ldg(T.target + t);
+      const c128 a = T.amp_complex ? make_c128(__ldg(T.amp + 2 * t), __ldg(T.amp + 2 * t + 1)) : make_c128(__ldg(T.amp + t), 0.0);
+      int64_t j = -1;
+      c128 v = a;
+      if (b2 == b) {
+        j = r;
+        v = cmul(cmul(a, a_self), inv_self);
+      } else {
+        const uint64_t mw = min_words[at];
+        const int gi = garg[at];
+        ++at;
+        if (rank_word_dyn(L, b2) >= 0) {
+          j = rank_reduced(R, mw);
+          if (j >= 0) {
+            const double inv_norm = 1.0 / sqrt((double)__ldg(R.orbit_size + j));
+            c128 a2 = make_c128(__ldg(S.chi + 2 * gi) * inv_norm, -__ldg(S.chi + 2 * gi + 1) * inv_norm);
+            if (conj_side) a2 = cconj(a2);
+            v = cmul(cmul(a, a2), inv_self);
+          }
+        }
+      }
+      raw_row[out] = j;
+      raw_val[out] = v;
+      ++out;
+    }
+  }
+}
+
 struct K6Scratch {
   DevBuf<int64_t> counts, offs;
   DevBuf<uint64_t> words;
@@ -277,6 +323,52 @@ struct K6Scratch {
 static K6Scratch& scratch() {
   static thread_local K6Scratch s;
   return s;
+}
+
+// Phases A + B for rows [row0, row0 + nb): sc.offs = exclusive offsets of the off-diagonal hits per row, sc.words = the
+// orbit minimum of every hit, sc.garg = the element the reference's Dict keeps for it.  Returns the number of hits.
+static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64_t nb, K6Scratch& sc, cudaEvent_t ev_mid) {
+  ed_rbasis* rb = o->rbasis;
+  ed_basis* parent = rb->parent;
+  const SymDesc S = rb->symdesc();
+  const int sm = ed_sm_count();
+  if (sc.counts.n < (size_t)nb + 1) { sc.counts.alloc((size_t)nb + 1); sc.offs.alloc((size_t)nb + 1); }
+  ED_CUDA(cudaMemsetAsync(sc.counts.p + nb, 0, sizeof(int64_t), ed_stream()));
+  const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 255) / 256, (int64_t)sm * 16));
+  ED_LAUNCH(k6a_count, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.counts.p);
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
+  if (sc.tmp.n < bytes) sc.tmp.alloc(bytes);
+  cub::DeviceScan::ExclusiveSum(sc.tmp.p, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  int64_t n_hits = 0;
+  ED_CUDA(cudaMemcpyAsync(&n_hits, sc.offs.p + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));
+  ED_CUDA(cudaStreamSynchronize(ed_stream()));
+  if (sc.words.n < (size_t)std::max<int64_t>(n_hits, 1)) {
+    sc.words.alloc((size_t)std::max<int64_t>(n_hits, 1));
+    sc.garg.alloc((size_t)std::max<int64_t>(n_hits, 1));
+  }
+  if (n_hits > 0) {
+    ED_LAUNCH(k6a_emit, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.offs.p, sc.words.p);
+    if (ev_mid) ED_CUDA(cudaEventRecord(ev_mid, ed_stream()));
+    const int grid_b = (int)((n_hits + 1023) / 1024);
+    const int nch = rb->symdev.n_chunks6;
+    const uint64_t* lut6 = rb->symdev.lut6.p;
+    const int32_t* inv = rb->symdev.inverse.p;
+    const SymDev& sd = rb->symdev;
+    if (sd.tr_on && nch <= 8) {
+      const size_t smem = (size_t)2 * 4 * nch * 64 * 8 + (size_t)2 * 4 * sd.tr_n1 * sd.tr_n2 * 4;
+      const int nb_ = parent->space.bits;
+      if (nch <= 4) ED_LAUNCH(k6b_canonicalize_tr<4>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+      else if (nch <= 6) ED_LAUNCH(k6b_canonicalize_tr<6>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+      else ED_LAUNCH(k6b_canonicalize_tr<8>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+    }
+    else if (nch <= 4) ED_LAUNCH(k6b_canonicalize<4>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+    else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+    else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+    else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+  }
+  return n_hits;
 }
 
 bool ed_apply_reduced_staged_supported(ed_oprep* o) {
@@ -317,42 +409,7 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
     if (timing) ED_CUDA(cudaEventRecord(ev[0], ed_stream()));
     const int64_t nb = std::min(batch_rows, n_rows - b0);
     const int64_t row0 = o->row_lo + b0;
-    if (sc.counts.n < (size_t)nb + 1) { sc.counts.alloc((size_t)nb + 1); sc.offs.alloc((size_t)nb + 1); }
-    ED_CUDA(cudaMemsetAsync(sc.counts.p + nb, 0, sizeof(int64_t), ed_stream()));
-    const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 255) / 256, (int64_t)sm * 16));
-    ED_LAUNCH(k6a_count, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.counts.p);
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
-    if (sc.tmp.n < bytes) sc.tmp.alloc(bytes);
-    cub::DeviceScan::ExclusiveSum(sc.tmp.p, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
-    g_launch_count.fetch_add(1, std::memory_order_relaxed);
-    int64_t n_hits = 0;
-    ED_CUDA(cudaMemcpyAsync(&n_hits, sc.offs.p + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));
-    ED_CUDA(cudaStreamSynchronize(ed_stream()));
-    if (sc.words.n < (size_t)std::max<int64_t>(n_hits, 1)) {
-      sc.words.alloc((size_t)std::max<int64_t>(n_hits, 1));
-      sc.garg.alloc((size_t)std::max<int64_t>(n_hits, 1));
-    }
-    if (n_hits > 0) {
-      ED_LAUNCH(k6a_emit, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.offs.p, sc.words.p);
-      if (timing) ED_CUDA(cudaEventRecord(ev[1], ed_stream()));
-      const int grid_b = (int)((n_hits + 1023) / 1024);
-      const int nch = rb->symdev.n_chunks6;
-      const uint64_t* lut6 = rb->symdev.lut6.p;
-      const int32_t* inv = rb->symdev.inverse.p;
-      const SymDev& sd = rb->symdev;
-      if (sd.tr_on && nch <= 8) {
-        const size_t smem = (size_t)2 * 4 * nch * 64 * 8 + (size_t)2 * 4 * sd.tr_n1 * sd.tr_n2 * 4;
-        const int nb_ = parent->space.bits;
-        if (nch <= 4) ED_LAUNCH(k6b_canonicalize_tr<4>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
-        else if (nch <= 6) ED_LAUNCH(k6b_canonicalize_tr<6>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
-        else ED_LAUNCH(k6b_canonicalize_tr<8>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
-      }
-      else if (nch <= 4) ED_LAUNCH(k6b_canonicalize<4>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
-      else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
-      else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
-      else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
-    }
+    const int64_t n_hits = k6_stage_batch(o, T, row0, nb, sc, timing ? ev[1] : nullptr);
     if (timing) ED_CUDA(cudaEventRecord(ev[2], ed_stream()));
     const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 127) / 128, (int64_t)grid_c_max));
     ED_LAUNCH(k6c_combine, grid_c, 128, 0, T, L, S, R, row0, nb, b0, sc.offs.p, sc.words.p, sc.garg.p,
@@ -370,4 +427,27 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
     for (auto& e : ev) cudaEventDestroy(e);
   }
   if (alpha_dot) ed_reduce_pairs(sc.partials.p, slots_used, alpha_dot);
+}
+
+// raw entries of lines [line0, line0 + n) of a reduced representation for the sparse assembly (sparse.cu)
+bool ed_reduced_fill_raw_staged(ed_oprep* o, int side, int64_t line0, int64_t n, const int64_t* raw_offs, int64_t* raw_row, void* raw_val) {
+  const ed_rbasis* rbc = o->rbasis;
+  if (!rbc || rbc->symdev.lut6.n == 0 || rbc->symdev.n_chunks6 > 11 || getenv("EDCUDA_K6_SIMPLE")) return false;
+  ed_upload_terms(o);
+  ed_rbasis* rb = o->rbasis;
+  ed_basis* parent = rb->parent;
+  if (parent->kind == ED_BASIS_LIST) parent->materialize();
+  const TermsDev& TD = side == ED_SIDE_LEFT ? o->terms_left : o->terms_right;
+  K6Terms T{TD.n_terms, TD.mask.p, TD.match.p, TD.target.p, TD.amp.p, TD.is_complex ? 1 : 0};
+  RLookupDesc R;
+  R.words = rb->words.p; R.orbit_size = rb->orbit_size.p; R.last_stab = rb->last_stab.p;
+  R.bucket_start = rb->bucket_start.p; R.bucket_shift = rb->bucket_shift; R.n_buckets = rb->n_buckets; R.dim = rb->dim;
+  const SymDesc S = rb->symdesc();
+  const LookupDesc L = parent->desc();
+  K6Scratch& sc = scratch();
+  k6_stage_batch(o, T, line0, n, sc, nullptr);
+  const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)ed_sm_count() * 16));
+  ED_LAUNCH(k6c_fill_raw, grid_c, 128, 0, T, L, S, R, line0, n, sc.offs.p, sc.words.p, sc.garg.p, side == ED_SIDE_RIGHT ? 1 : 0,
+            raw_offs, raw_row, reinterpret_cast<c128*>(raw_val));
+  return true;
 }

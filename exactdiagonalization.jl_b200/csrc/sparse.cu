@@ -149,7 +149,10 @@ static void assemble_lines(ed_oprep* o, double tol, int side, int64_t lo, int64_
     ED_CUDA(cudaStreamSynchronize(ed_stream()));
     raw_row.alloc((size_t)std::max<int64_t>(raw_total, 1));
     raw_val.alloc((size_t)std::max<int64_t>(raw_total, 1));
-    ED_LAUNCH(k4_fill_raw, grid, 128, 0, W, lo + c0, nc, offs.p, raw_row.p, raw_val.p);
+    // reduced representations with enough lines: orbit minima from the word-parallel staged sweep (reduced_staged.cu)
+    const int64_t staged_min = getenv("EDCUDA_K6_MIN_ROWS") ? atoll(getenv("EDCUDA_K6_MIN_ROWS")) : 2048;
+    if (!(o->rbasis && nc >= staged_min && ed_reduced_fill_raw_staged(o, side, lo + c0, nc, offs.p, raw_row.p, raw_val.p)))
+      ED_LAUNCH(k4_fill_raw, grid, 128, 0, W, lo + c0, nc, offs.p, raw_row.p, raw_val.p);
     ED_LAUNCH(k4_merge_chop, grid, 128, 0, nc, offs.p, raw_row.p, raw_val.p, tol, cplx, kept.p);
     exclusive_scan(kept.p, out_offs.p, nc + 1, tmp);
     int64_t nnz_b = 0;

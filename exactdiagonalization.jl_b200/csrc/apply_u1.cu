@@ -71,6 +71,9 @@ struct U1Params {
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
+  int far_bit;                  // bonds whose upper H bit is >= far_bit read their neighbour tile with evict-first loads:
+                                // its re-use distance (2^(bit+1) tiles) exceeds the L2, so the line is a one-shot
+
   const uint32_t* tile_order;   // optional launch order (whole-basis launches): position -> index into tile_H
   // x as up to ED_MAX_SEG contiguous, tile-aligned segments (local memory or peer GPUs' memory mapped over NVLink)
   int n_seg;
@@ -115,6 +118,27 @@ __device__ __forceinline__ c128 vec_scale<c128>(double a, c128 v) { return make_
 __device__ __forceinline__ void vec_fma(double& acc, double a, double v) { acc = fma(a, v, acc); }
 __device__ __forceinline__ void vec_fma(c128& acc, double a, c128 v) { acc.re = fma(a, v.re, acc.re); acc.im = fma(a, v.im, acc.im); }
 __device__ __forceinline__ double vec_add(double a, double b) { return a + b; }
+// one-shot reads of far tiles: streaming (evict-first) loads so that they do not push the re-used near tiles out of L2
+__device__ __forceinline__ double ldcs_val(const double* p) { return __ldcs(p); }
+__device__ __forceinline__ c128 ldcs_val(const c128* p) { const double2 v = __ldcs(reinterpret_cast<const double2*>(p)); return make_c128(v.x, v.y); }
+// the same load instruction for both kinds of tile, the L2 eviction priority in a (warp-uniform) policy register
+__device__ __forceinline__ uint64_t l2_policy(int kind) {   // 0 normal, 1 evict first, 2 evict last
+  uint64_t pol;
+  if (kind == 1) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ld_hint(const double* p, uint64_t pol) {
+  double v;
+  asm("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ c128 ld_hint(const c128* p, uint64_t pol) {
+  c128 v;
+  asm("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.re), "=d"(v.im) : "l"(p), "l"(pol));
+  return v;
+}
 // y is written once and never re-read by this kernel: streaming (evict-first) stores keep L2 for x
 __device__ __forceinline__ void st_stream(double* p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream(c128* p, c128 v) { __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im)); }
@@ -190,15 +214,18 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
 #pragma unroll 1
   for (int e = 0; e < T.n_hh; ++e) {
     const double a = T.hh_amp[e];
-    const VecT* xe = T.hh_ptr[e];
+    const uintptr_t tagged = reinterpret_cast<uintptr_t>(T.hh_ptr[e]);
+    const bool far = tagged & 1u;                        // warp-uniform: one-shot read of a far tile
+    const VecT* xe = reinterpret_cast<const VecT*>(tagged & ~(uintptr_t)1u);
     const VecT* xt = xe + tid;
-    const VecT vt = ldg_val(xe + it);
+    const uint64_t pol = l2_policy(far ? 1 : 0);
+    const VecT vt = ld_hint(xe + it, pol);
 #pragma unroll
     for (int r0 = 0; r0 < NF; r0 += CH) {
       VecT v[CH];
 #pragma unroll
       for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) v[c] = ldg_val(xt + (r0 + c) * THREADS);
+        if (r0 + c < NF) v[c] = ld_hint(xt + (r0 + c) * THREADS, pol);
 #pragma unroll
       for (int c = 0; c < CH; ++c)
         if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
@@ -258,10 +285,12 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
   for (int e = 0; e < T.n_mx; ++e) {
     const uint16_t* tab = P.mx_tab + T.mx_toff[e];
     const uint16_t* tt = tab + tid;
-    const VecT* xe = T.mx_ptr[e];
+    const uintptr_t tagged = reinterpret_cast<uintptr_t>(T.mx_ptr[e]);
+    const VecT* xe = reinterpret_cast<const VecT*>(tagged & ~(uintptr_t)1u);
+    const uint64_t pol = l2_policy((tagged & 1u) ? 1 : 0);
     const double a = T.mx_amp[e];
     const uint32_t jt = __ldg(tab + it);
-    const VecT vt = jt != 0xFFFFu ? ldg_val(xe + jt) : vzero((VecT*)nullptr);
+    const VecT vt = jt != 0xFFFFu ? ld_hint(xe + jt, pol) : vzero((VecT*)nullptr);
 #pragma unroll
     for (int r0 = 0; r0 < NF; r0 += CH) {
       uint32_t j[CH];
@@ -271,7 +300,7 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
         if (r0 + c < NF) j[c] = __ldg(tt + (r0 + c) * THREADS);
 #pragma unroll
       for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) v[c] = j[c] != 0xFFFFu ? ldg_val(xe + j[c]) : vzero((VecT*)nullptr);
+        if (r0 + c < NF) v[c] = j[c] != 0xFFFFu ? ld_hint(xe + j[c], pol) : vzero((VecT*)nullptr);
 #pragma unroll
       for (int c = 0; c < CH; ++c)
         if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
@@ -357,7 +386,8 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (fire) {
         const int slot = n + __popc(m & ((1u << tid) - 1u));
-        hh_ptr[slot] = u1_seg_resolve<VecT>(P, P.tile_base[H2]);
+        const uintptr_t ptr = reinterpret_cast<uintptr_t>(u1_seg_resolve<VecT>(P, P.tile_base[H2]));
+        hh_ptr[slot] = reinterpret_cast<const VecT*>(ptr | ((int)P.hh_q[b] >= P.far_bit ? 1u : 0u));
         hh_amp[slot] = P.hh_amp[b];
       }
       n += __popc(m);
@@ -368,7 +398,8 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
     for (int b = lane; b < P.n_mx; b += 32) {
       const int q = P.mx_q[b];
       const uint32_t hbit = (H >> q) & 1u;
-      mx_ptr[b] = u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)]);
+      mx_ptr[b] = reinterpret_cast<const VecT*>(reinterpret_cast<uintptr_t>(u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)])) |
+                                                (q >= P.far_bit ? 1u : 0u));
       mx_amp[b] = P.mx_amp[b];
       mx_toff[b] = ((uint32_t)(2 * b + hbit) << k) + lofs;
     }
@@ -773,6 +804,14 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   }
   P.tile_cap = tile_cap;
   plan->n_tiles = (int)tile_H.size();
+  {
+    int dev = 0, l2 = 0;
+    ED_CUDA(cudaGetDevice(&dev));
+    ED_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
+    const double tile_bytes = (double)tile_cap * vec_bytes;
+    P.far_bit = 0;
+    while (P.far_bit < hb && std::ldexp(tile_bytes, P.far_bit + 1) <= (double)l2) ++P.far_bit;
+  }
   // optional launch order for whole-basis launches: tiles grouped by a window of "slow" H bits, so that the tiles
   // running at the same time are closed under the bonds on the remaining (fast) bits -- including the periodic bond,
   // whose H bit is the top one -- and find each other's x in L2.  EDCUDA_U1_ORDER="first_slow_bit,n_slow_bits".
@@ -876,6 +915,8 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   P.accumulate = accumulate;
   // profiling knob (results are WRONG when set): drop parts of the kernel to measure what each costs
   static const int ablate = getenv("EDCUDA_U1_ABLATE") ? atoi(getenv("EDCUDA_U1_ABLATE")) : 0;
+  static const int far_bit = getenv("EDCUDA_U1_FARBIT") ? atoi(getenv("EDCUDA_U1_FARBIT")) : -1;   // override of the plan's choice
+  if (far_bit >= 0) P.far_bit = far_bit;
   if (ablate & 1) P.n_ll = 0;
   if (ablate & 2) P.n_hh = 0;
   if (ablate & 4) P.n_mx = 0;

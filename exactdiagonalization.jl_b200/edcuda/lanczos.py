@@ -82,7 +82,7 @@ class RowSharding:
         self.lo, self.hi = self.ranges[rank]
         self.max_rows = max(h - l for l, h in self.ranges)
         self.uniform = all(h - l == self.max_rows for l, h in self.ranges)
-        self.x_full = torch.zeros(dim, dtype=t_dtype, device=device)
+        self.x_full = torch.zeros(dim if world > 1 else 0, dtype=t_dtype, device=device)
         if not self.uniform:
             self.x_pad = torch.zeros(self.max_rows * world, dtype=t_dtype, device=device)
             self.send = torch.zeros(self.max_rows, dtype=t_dtype, device=device)
@@ -91,7 +91,7 @@ class RowSharding:
         """all-gather the rank-local rows into the full-length vector."""
         dist = self.dist
         if self.world == 1:
-            self.x_full.copy_(x_local)
+            return x_local                    # one rank owns every row: the local vector is the full vector, no copy
         elif self.uniform:
             dist.all_gather_into_tensor(self.x_full, x_local, group=self.group)
         else:

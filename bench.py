@@ -311,13 +311,16 @@ def main():
     opr = ed.represent(hsr, h).set_kernel(args.kernel)
     p2p = world > 1 and args.exchange == "p2p" and args.kernel == 0
     mv = P2PShardedMatvec(opr, rank, world, np.float64, n_buffers=1) if p2p else ShardedMatvec(opr, rank, world, np.float64)
-    n_local = mv.hi - mv.lo
+    n_local = mv.n_local
+    mv_ranges = list(mv.local_ranges)
     # synthetic input: Philox normal vector keyed by the global row index (shard-count independent)
     x_local = mv.x_buffer(0) if p2p else torch.empty(n_local, dtype=torch.float64, device=dev)
     y_local = torch.zeros(n_local, dtype=torch.float64, device=dev)
     import ctypes as C
     check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
-    check(lib.ed_vector_randn_async(x_local.data_ptr(), n_local, ed.ED_F64, 20260717 + 5, mv.lo))
+    for lo_, hi_, off_ in mv.local_ranges:
+        if hi_ > lo_:
+            check(lib.ed_vector_randn_async(x_local[off_:].data_ptr(), hi_ - lo_, ed.ED_F64, 20260717 + 5, lo_))
     lib.ed_set_stream(None, 0)
     x_local.mul_(1.0 / math.sqrt(dim))
     torch.cuda.synchronize()
@@ -458,7 +461,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "gnnz_per_s": nnz_eff(n, n_bonds) * value / 1e9,
             "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": dim, "n_terms": len(h.terms),
-                       "rows_per_gpu": n_local, "sharding": "rows" if world > 1 else "none",
+                       "rows_per_gpu": n_local, "sharding": ("rows" if world > 1 else "none") + (", two wrap-aware ranges per rank" if len(mv_ranges) > 1 else ""),
                        "exchange": ("none" if world == 1 else "peer loads of far-bond tiles over NVLink inside the kernel (CUDA IPC), "
                                     "stream-ordered NCCL fence per matvec" if p2p_used else "nccl all_gather of x per matvec"),
                        "l2": "inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (dim * 8 / 1e9),

@@ -106,6 +106,8 @@ struct FastU1Plan {
   DevBuf<double> partials;
   std::vector<uint64_t> h_base, h_size;  // per non-empty tile, ascending
   bool order_on = false;
+  bool wraps = false;       // a tabulated straddler flips the top site (the periodic bond of a ring)
+  int hb = 0;               // bits of H
 };
 
 template <typename T>
@@ -828,6 +830,10 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
     }
   }
 
+  plan->hb = hb;
+  plan->wraps = false;
+  for (int e = 0; e < P.n_mx; ++e) plan->wraps |= (int)mx_q[e] == hb - 1;
+
   auto nonempty8 = [](std::vector<uint8_t>& v) { if (v.empty()) v.push_back(0); };
   auto nonemptyd = [](std::vector<double>& v) { if (v.empty()) v.push_back(0.0); };
   nonempty8(hh_p); nonempty8(hh_q); nonempty8(mx_q); nonempty8(mq_p); nonempty8(mq_q); nonempty8(ms_q); nonempty8(mq_pidx);
@@ -903,6 +909,45 @@ void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo
   };
   *lo = snap(dim / world * rank + std::min<int64_t>(rank, dim % world));
   *hi = snap(dim / world * (rank + 1) + std::min<int64_t>(rank + 1, dim % world));
+}
+
+// Wrap-aware shards.  With contiguous single ranges the bond that wraps around the top site (periodic bond of a ring)
+// always lands on another rank, as an 8-byte gather that wastes half of every NVLink sector.  Giving every rank the
+// SAME range of the remaining high bits in both halves of the basis (top site empty / occupied) keeps that bond local:
+// two tile-aligned row ranges per rank, balanced by their combined row count.  Returns 2 ranges, or 1 (the plain
+// split) when the operator has no such bond or the world is too large for the tile grid.
+int ed_u1_suggest_rows2(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi) {
+  FastU1Plan* plan = get_plan(o, dtype);
+  const int hb = plan->hb;
+  if (!plan->supported || !plan->wraps || hb < 2 || world < 2 || (1 << (hb - 1)) < 4 * world || getenv("EDCUDA_U1_NOWRAPSHARD")) {
+    ed_u1_suggest_rows(o, dtype, world, rank, lo, hi);
+    return 1;
+  }
+  const U1Params& P = plan->P;
+  const uint32_t top = 1u << (hb - 1);
+  auto tile_rows = [&](uint32_t H) -> uint64_t {
+    const int pl = P.n_set - __builtin_popcount(H);
+    return (pl < 0 || pl > P.k) ? 0ull : binom_u64(P.k, pl);
+  };
+  // prefix[h] = rows of the tiles h' < h in the lower half, and the same for the upper half
+  std::vector<uint64_t> pre_lo(top + 1, 0), pre_hi(top + 1, 0);
+  for (uint32_t h = 0; h < top; ++h) {
+    pre_lo[h + 1] = pre_lo[h] + tile_rows(h);
+    pre_hi[h + 1] = pre_hi[h] + tile_rows(h | top);
+  }
+  const uint64_t total = pre_lo[top] + pre_hi[top];
+  auto cut = [&](int r) -> uint32_t {   // first h whose combined prefix reaches r/world of all rows
+    if (r <= 0) return 0;
+    if (r >= world) return top;
+    const uint64_t target = total / (uint64_t)world * (uint64_t)r;
+    uint32_t a = 0, b = top;
+    while (a < b) { const uint32_t m = (a + b) / 2; if (pre_lo[m] + pre_hi[m] < target) a = m + 1; else b = m; }
+    return a;
+  };
+  const uint32_t h0 = cut(rank), h1 = cut(rank + 1);
+  lo[0] = (int64_t)pre_lo[h0]; hi[0] = (int64_t)pre_lo[h1];
+  lo[1] = (int64_t)(pre_lo[top] + pre_hi[h0]); hi[1] = (int64_t)(pre_lo[top] + pre_hi[h1]);
+  return 2;
 }
 
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {

@@ -305,6 +305,7 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side);                   
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate,
                  double* alpha_dot);
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
+int ed_u1_suggest_rows2(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);   // apply_u1.cu
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
                       double* alpha_dot);
 bool ed_apply_reduced_linear_supported(ed_oprep* o);                                            // reduced_linear.cu

@@ -174,6 +174,22 @@ int ed_oprep_suggest_rows(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t
   ED_CATCH
 }
 
+int ed_oprep_suggest_row_ranges(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi,
+                                int32_t* n_ranges) {
+  ED_TRY
+  ED_REQUIRE(oprep && row_lo && row_hi && n_ranges, ED_ERR_ARGUMENT, "null argument");
+  ED_REQUIRE(world >= 1 && rank >= 0 && rank < world, ED_ERR_ARGUMENT, "bad rank / world");
+  if (!oprep->rbasis && oprep->kernel_choice == 0 && ed_device_count() > 0 && ed_apply_u1_supported(oprep, dtype, ED_SIDE_LEFT)) {
+    *n_ranges = ed_u1_suggest_rows2(oprep, dtype, world, rank, row_lo, row_hi);
+  } else {
+    const int rc = ed_oprep_suggest_rows(oprep, dtype, world, rank, row_lo, row_hi);
+    ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
+    *n_ranges = 1;
+  }
+  if (*n_ranges == 1) { row_lo[1] = row_hi[0]; row_hi[1] = row_hi[0]; }
+  ED_CATCH
+}
+
 int ed_oprep_set_x_segments(ed_oprep* oprep, int32_t n_seg, const int64_t* seg_lo, const void* const* seg_ptr) {
   ED_TRY
   ED_REQUIRE(oprep, ED_ERR_ARGUMENT, "null argument");

@@ -96,6 +96,7 @@ SIGNATURES = {
     "ed_oprep_dtype": (C.c_int, [vp, P(i32)]),
     "ed_oprep_set_rows": (C.c_int, [vp, i64, i64]),
     "ed_oprep_suggest_rows": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64)]),
+    "ed_oprep_suggest_row_ranges": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64), P(i32)]),
     "ed_oprep_set_x_segments": (C.c_int, [vp, i32, vp, vp]),
     "ed_oprep_set_kernel": (C.c_int, [vp, i32]),
     "ed_apply": (C.c_int, [vp, vp, i64, vp, i64, i32, i32, i32]),

@@ -119,6 +119,8 @@ class ShardedMatvec:
         self.dist = self.sharding.dist
         self.ranges = self.sharding.ranges
         self.lo, self.hi = self.sharding.lo, self.sharding.hi
+        self.local_ranges = [(self.lo, self.hi, 0)]      # (global lo, global hi, offset in the local vector)
+        self.n_local = self.hi - self.lo
         opr.set_rows(self.lo, self.hi)
 
     @property
@@ -174,8 +176,11 @@ class DeviceBuffer:
 class P2PShardedMatvec:
     """Row-sharded y = H x WITHOUT an all-gather: every rank keeps its rows of x in a buffer that the other ranks map
     through CUDA IPC, and the matvec kernel pulls the few neighbour tiles it needs straight over NVLink (peer loads),
-    overlapped with its local work.  Shards are tile aligned (ed_oprep_suggest_rows).  `n_buffers` shared buffers are
-    kept so that a Lanczos loop can ping-pong between them.  Only the U(1) fast-path kernel consumes segmented inputs."""
+    overlapped with its local work.  Shards are tile aligned and wrap aware (ed_oprep_suggest_row_ranges): for a ring
+    every rank owns the same range of high bits in BOTH halves of the basis (top site empty / occupied), i.e. two row
+    ranges stored back to back in its local vectors, so that the periodic bond never leaves the rank.  `n_buffers`
+    shared buffers are kept so that a Lanczos loop can ping-pong between them.  Only the U(1) fast-path kernel consumes
+    segmented inputs."""
 
     def __init__(self, opr, rank: int, world: int, dtype=None, group=None, n_buffers: int = 2):
         import torch
@@ -187,14 +192,19 @@ class P2PShardedMatvec:
         self.t_dtype = torch.complex128 if self.np_dtype == np.complex128 else torch.float64
         self.code = ED_C128 if self.np_dtype == np.complex128 else ED_F64
         self.dev = torch.device("cuda", torch.cuda.current_device())
-        self.ranges = []
+        self.rank_ranges = []          # per rank: its 1 or 2 (lo, hi) row ranges
         for r in range(world):
-            lo, hi = C.c_int64(), C.c_int64()
-            check(lib.ed_oprep_suggest_rows(opr._handle, self.code, world, r, C.byref(lo), C.byref(hi)))
-            self.ranges.append((lo.value, hi.value))
-        self.lo, self.hi = self.ranges[rank]
-        opr.set_rows(self.lo, self.hi)
-        n_local = self.hi - self.lo
+            lo, hi, n = (C.c_int64 * 2)(), (C.c_int64 * 2)(), C.c_int32()
+            check(lib.ed_oprep_suggest_row_ranges(opr._handle, self.code, world, r, lo, hi, C.byref(n)))
+            self.rank_ranges.append([(lo[i], hi[i]) for i in range(n.value)])
+        self.local_ranges, off = [], 0   # (global lo, global hi, offset in the local vector)
+        for lo, hi in self.rank_ranges[rank]:
+            self.local_ranges.append((lo, hi, off))
+            off += hi - lo
+        self.n_local = off
+        self.lo, self.hi = self.rank_ranges[rank][0]
+        self.ranges = [rr[0] for rr in self.rank_ranges]
+        n_local = self.n_local
         self.bufs = [DeviceBuffer(n_local, self.np_dtype) for _ in range(n_buffers)]
         self.views = [b.tensor() for b in self.bufs]
         for v in self.views:
@@ -207,7 +217,7 @@ class P2PShardedMatvec:
         else:
             allh = [mine]
         self._opened = []
-        self.seg_ptr = []      # per buffer: pointer of every rank's shard as seen from this process
+        base_ptr = []      # per buffer: base pointer of every rank's local vector as seen from this process
         for b in range(n_buffers):
             ptrs = []
             for r in range(world):
@@ -218,12 +228,24 @@ class P2PShardedMatvec:
                     check(lib.ed_ipc_open_handle((C.c_uint8 * 64).from_buffer_copy(allh[r][b]), C.byref(p)))
                     self._opened.append(p.value)
                     ptrs.append(p.value)
-            self.seg_ptr.append(ptrs)
-        self.seg_lo = (C.c_int64 * (world + 1))(*([r[0] for r in self.ranges] + [self.dim]))
+            base_ptr.append(ptrs)
+        # segments in ascending global row order: (lo, rank, byte offset inside that rank's vector)
+        segs = []
+        for r, rr in enumerate(self.rank_ranges):
+            o = 0
+            for lo, hi in rr:
+                if hi > lo:
+                    segs.append((lo, r, o * self.np_dtype.itemsize))
+                o += hi - lo
+        segs.sort()
+        self.n_seg = len(segs)
+        self.seg_lo = (C.c_int64 * (self.n_seg + 1))(*([s_[0] for s_ in segs] + [self.dim]))
+        self.seg_ptr = [[base_ptr[b][r] + o for (_, r, o) in segs] for b in range(n_buffers)]
         self._token = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._dot_tmp = torch.zeros(2, 2, dtype=torch.float64, device=self.dev)
 
     def x_buffer(self, which: int = 0):
-        """This rank's rows of shared input buffer `which` (a torch tensor; write x here)."""
+        """This rank's rows of shared input buffer `which` (a torch tensor; write x here; layout = local_ranges)."""
         return self.views[which]
 
     def fence(self):
@@ -233,15 +255,25 @@ class P2PShardedMatvec:
 
     def matvec(self, y_local, which: int = 0, dot_out=None):
         torch = self.torch
-        ptrs = (C.c_void_p * self.world)(*self.seg_ptr[which])
-        check(lib.ed_oprep_set_x_segments(self.opr._handle, self.world, self.seg_lo, ptrs))
+        ptrs = (C.c_void_p * self.n_seg)(*self.seg_ptr[which])
+        check(lib.ed_oprep_set_x_segments(self.opr._handle, self.n_seg, self.seg_lo, ptrs))
         check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+        two = len(self.local_ranges) > 1
         try:
-            check(lib.ed_apply_async(self.opr._handle, y_local.data_ptr(), None, self.code, ED_SIDE_LEFT, 0,
-                                     dot_out.data_ptr() if dot_out is not None else None))
+            for i, (lo, hi, off) in enumerate(self.local_ranges):
+                self.opr.set_rows(lo, hi)
+                dot = None if dot_out is None else (self._dot_tmp[i] if two else dot_out)
+                if hi <= lo:
+                    if dot is not None:
+                        dot.zero_()
+                    continue
+                check(lib.ed_apply_async(self.opr._handle, y_local[off:].data_ptr(), None, self.code, ED_SIDE_LEFT, 0,
+                                         dot.data_ptr() if dot is not None else None))
         finally:
             lib.ed_set_stream(None, 0)
             lib.ed_oprep_set_x_segments(self.opr._handle, 0, None, None)
+        if two and dot_out is not None:
+            torch.add(self._dot_tmp[0], self._dot_tmp[1], out=dot_out)
         return y_local
 
     def close(self):
@@ -262,7 +294,7 @@ class ShardedLanczos:
         self.p2p = exchange == "p2p"
         self.mv = P2PShardedMatvec(opr, rank, world, dtype, group) if self.p2p else ShardedMatvec(opr, rank, world, dtype, group)
         torch = self.mv.torch
-        n = self.mv.hi - self.mv.lo
+        n = self.mv.n_local
         self.n_local = n
         mk = lambda: torch.zeros(max(n, 1), dtype=self.mv.t_dtype, device=self.mv.dev)[:n]
         if self.p2p:
@@ -285,7 +317,9 @@ class ShardedLanczos:
             if v0_local is not None:
                 self.u_cur.copy_(v0_local)
             else:
-                check(lib.ed_vector_randn_async(self.u_cur.data_ptr(), self.n_local, mv.code, seed, mv.lo))
+                for lo, hi, off in mv.local_ranges:      # keyed by the global row index: shard-count independent
+                    if hi > lo:
+                        check(lib.ed_vector_randn_async(self.u_cur[off:].data_ptr(), hi - lo, mv.code, seed, lo))
             check(lib.ed_vector_norm2_async(self.u_cur.data_ptr(), self.n_local, mv.code, norms[0].data_ptr()))
         finally:
             lib.ed_set_stream(None, 0)

@@ -184,6 +184,14 @@ int ed_oprep_set_rows(ed_oprep* oprep, int64_t row_lo, int64_t row_hi);
 /* Row range rank `rank` of `world` should own: the reference's balanced splitrange (src/util.jl:102-121) with the
  * boundaries snapped to the fast kernel's tile boundaries, so that segmented inputs (below) are tile aligned. */
 int ed_oprep_suggest_rows(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi);
+/* Like ed_oprep_suggest_rows, but a rank may receive TWO row ranges (row_lo[2], row_hi[2], *n_ranges = 2): when the
+ * operator has a bond that wraps around the most significant site (the periodic bond of a ring), every rank gets the same
+ * range of the remaining high bits in both halves of the basis, which keeps that bond -- otherwise an 8-byte gather from a
+ * peer GPU -- rank-local.  The ranges are tile aligned; apply them one after the other with ed_oprep_set_rows.
+ * *n_ranges = 1: same answer as ed_oprep_suggest_rows (second range empty).  Not in the reference (no multi-device path;
+ * its threads split rows with splitrange, src/util.jl:102-121). */
+int ed_oprep_suggest_row_ranges(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi,
+                                int32_t* n_ranges);
 /* Hand the input vector over as n_seg (<= 16) contiguous segments instead of one pointer: segment s holds rows
  * [seg_lo[s], seg_lo[s+1]) at device address seg_ptr[s] (local memory or a peer GPU's buffer opened with
  * ed_ipc_open_handle).  While set, ed_apply_async ignores its `x` argument.  n_seg = 0 clears.  Only the U(1)

@@ -878,13 +878,17 @@ def _nccl_worker(rank, world, port, q):
     res_p = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="p2p").run(120, seed=4)
     pm = P2PShardedMatvec(ed.represent(hsr, h), rank, world, n_buffers=1)
     xp = pm.x_buffer(0)
-    xp.copy_(torch.arange(pm.lo, pm.hi, dtype=torch.float64, device="cuda").sin())
+    for lo, hi, off in pm.local_ranges:
+        xp[off:off + hi - lo].copy_(torch.arange(lo, hi, dtype=torch.float64, device="cuda").sin())
     yp = torch.zeros_like(xp)
+    dotp = torch.zeros(2, dtype=torch.float64, device="cuda")
     pm.fence()
-    pm.matvec(yp, 0)
+    pm.matvec(yp, 0, dotp)
     torch.cuda.synchronize()
-    yps = [None] * world
-    dist.all_gather_object(yps, yp.cpu().numpy())
+    assert abs(float(dotp[0]) - float(torch.dot(xp, yp))) < 1e-9 * float(xp.norm() * yp.norm())
+    parts = [None] * world          # (global lo, rows) of every range of every rank -> assembled in global row order
+    dist.all_gather_object(parts, [(lo, yp[off:off + hi - lo].cpu().numpy()) for lo, hi, off in pm.local_ranges])
+    yps = [a for _, a in sorted([p for pr in parts for p in pr], key=lambda t: t[0])]
     pm.close()
     mv = ShardedMatvec(ed.represent(hsr, h), rank, world)
     x = torch.arange(mv.lo, mv.hi, dtype=torch.float64, device="cuda").sin()

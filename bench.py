@@ -260,7 +260,7 @@ def main():
     ap.add_argument("--impl", default="edcuda")
     ap.add_argument("--workload", default="xxz_chain_L32_sz0")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"],
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "dma", "allgather"],
                     help="N>1: how remote rows of x reach a rank: peer loads over NVLink inside the kernel (p2p) or an NCCL all-gather per matvec")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -309,8 +309,8 @@ def main():
     hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
     dim = hsr.dimension
     opr = ed.represent(hsr, h).set_kernel(args.kernel)
-    p2p = world > 1 and args.exchange == "p2p" and args.kernel == 0
-    mv = P2PShardedMatvec(opr, rank, world, np.float64, n_buffers=1) if p2p else ShardedMatvec(opr, rank, world, np.float64)
+    p2p = world > 1 and args.exchange in ("p2p", "dma") and args.kernel == 0
+    mv = P2PShardedMatvec(opr, rank, world, np.float64, n_buffers=1, exchange=args.exchange) if p2p else ShardedMatvec(opr, rank, world, np.float64)
     n_local = mv.n_local
     mv_ranges = list(mv.local_ranges)
     # synthetic input: Philox normal vector keyed by the global row index (shard-count independent)
@@ -433,7 +433,7 @@ def main():
         del mv
         torch.cuda.empty_cache()
         sl = ShardedLanczos(ed.represent(hsr, h).set_kernel(args.kernel), rank, world, np.float64,
-                            exchange="p2p" if (world > 1 and args.exchange == "p2p" and args.kernel == 0) else "allgather")
+                            exchange=args.exchange if (world > 1 and args.exchange in ("p2p", "dma") and args.kernel == 0) else "allgather")
         sl.run(3, seed=1)            # warm-up
         barrier()
         t0 = time.perf_counter()
@@ -462,7 +462,10 @@ def main():
             "gnnz_per_s": nnz_eff(n, n_bonds) * value / 1e9,
             "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": dim, "n_terms": len(h.terms),
                        "rows_per_gpu": n_local, "sharding": ("rows" if world > 1 else "none") + (", two wrap-aware ranges per rank" if len(mv_ranges) > 1 else ""),
-                       "exchange": ("none" if world == 1 else "peer loads of far-bond tiles over NVLink inside the kernel (CUDA IPC), "
+                       "exchange": ("none" if world == 1 else
+                                    "split: copy engines pull the needed peer rows into a mirror vector during a rank-local kernel pass, a second pass adds them (CUDA IPC), "
+                                    "stream-ordered NCCL fence per matvec" if (p2p_used and args.exchange == "dma") else
+                                    "peer loads of far-bond tiles over NVLink inside the kernel (CUDA IPC), "
                                     "stream-ordered NCCL fence per matvec" if p2p_used else "nccl all_gather of x per matvec"),
                        "l2": "inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (dim * 8 / 1e9),
                        "kernel": "generic term-walk" if args.kernel == 1 else "auto",

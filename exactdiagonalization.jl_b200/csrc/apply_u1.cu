@@ -71,6 +71,12 @@ struct U1Params {
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
+  // split exchange (multi-GPU): stream_mode 1 = LOCAL pass (neighbour streams whose tile lives in a peer segment are
+  // skipped), 2 = REMOTE pass (only those streams, read from `mirror` -- a full-length local vector whose needed remote
+  // rows were filled by copy engines meanwhile -- and added to y); 0 = everything in one pass through the segments
+  int stream_mode;
+  uint32_t local_seg_mask;      // bit s: segment s is this rank's own memory
+  const void* mirror;
   int far_bit;                  // bonds whose upper H bit is >= far_bit read their neighbour tile with evict-first loads:
                                 // its re-use distance (2^(bit+1) tiles) exceeds the L2, so the line is a one-shot
 
@@ -86,6 +92,26 @@ __device__ __forceinline__ const VecT* u1_seg_resolve(const U1Params& P, uint64_
   int s = 0;
   while (s + 1 < P.n_seg && (int64_t)idx >= P.seg_lo[s + 1]) ++s;
   return reinterpret_cast<const VecT*>(P.seg_ptr[s]) + ((int64_t)idx - P.seg_lo[s]);
+}
+
+template <typename VecT>
+__device__ __forceinline__ const VecT* u1_seg_resolve(const U1Params& P, uint64_t idx, int& seg) {
+  int s = 0;
+  while (s + 1 < P.n_seg && (int64_t)idx >= P.seg_lo[s + 1]) ++s;
+  seg = s;
+  return reinterpret_cast<const VecT*>(P.seg_ptr[s]) + ((int64_t)idx - P.seg_lo[s]);
+}
+
+// neighbour tile starting at global row `idx` under the exchange mode: false = this pass does not read it
+template <typename VecT>
+__device__ __forceinline__ bool u1_neighbour(const U1Params& P, uint64_t idx, const VecT*& ptr) {
+  int seg;
+  ptr = u1_seg_resolve<VecT>(P, idx, seg);
+  if (P.stream_mode == 0) return true;
+  const bool local = (P.local_seg_mask >> seg) & 1u;
+  if (P.stream_mode == 1) return local;
+  ptr = reinterpret_cast<const VecT*>(P.mirror) + idx;
+  return !local;
 }
 
 struct FastU1Plan {
@@ -182,7 +208,11 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     const double* dl = P.dlow + T.lofs;
     double dd[NF > 0 ? NF : 1];
     double dt = T.d_tile;
-    if (P.diag_mode == 1) {
+    if (P.stream_mode == 2) {                    // remote pass: only the contributions of the peer tiles
+#pragma unroll
+      for (int r = 0; r < NF; ++r) dd[r] = 0.0;
+      dt = 0.0;
+    } else if (P.diag_mode == 1) {
       uint32_t code[NF > 0 ? NF : 1];
 #pragma unroll
       for (int r = 0; r < NF; ++r) code[r] = __ldg(dc + tid + r * THREADS);
@@ -198,7 +228,7 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
 #pragma unroll
       for (int r = 0; r < NF; ++r) dd[r] = T.d_tile;
     }
-    if (T.n_mq) {
+    if (T.n_mq && P.stream_mode != 2) {
       const uint16_t* lw = P.lowword + T.lofs;
 #pragma unroll
       for (int r = 0; r <= NF; ++r) {
@@ -318,17 +348,19 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     const int64_t row = row0 + r * THREADS;
     if (!whole && (row < P.row_lo || row >= P.row_hi)) continue;
     VecT out = acc[r];
+    if (want_dot && P.stream_mode == 2) dot_acc(dre, dim_, xs[tid + r * THREADS], out);
     if (P.accumulate) out = vec_add(out, yt[r * THREADS]);
     st_stream(yt + r * THREADS, out);
-    if (want_dot) dot_acc(dre, dim_, xs[tid + r * THREADS], out);
+    if (want_dot && P.stream_mode != 2) dot_acc(dre, dim_, xs[tid + r * THREADS], out);
   }
   const int64_t row = (int64_t)T.base + i_tail;
   if (tail_ok && (whole || (row >= P.row_lo && row < P.row_hi))) {
     VecT* dst = y + (row - P.row_lo);
     VecT out = acc_t;
+    if (want_dot && P.stream_mode == 2) dot_acc(dre, dim_, xs[i_tail], out);
     if (P.accumulate) out = vec_add(out, *dst);
     st_stream(dst, out);
-    if (want_dot) dot_acc(dre, dim_, xs[i_tail], out);
+    if (want_dot && P.stream_mode != 2) dot_acc(dre, dim_, xs[i_tail], out);
   }
 }
 
@@ -363,7 +395,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   uint32_t* ms_len = ms_lo + U1_MAX_MS;
   double* ms_amp = reinterpret_cast<double*>(ms_len + U1_MAX_MS);
   const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + U1_MAX_MS);
-  __shared__ int s_counts[2];
+  __shared__ int s_counts[4];
 
   const int tid = threadIdx.x;
   const uint32_t H = P.tile_H[P.tile_order ? P.tile_order[blockIdx.x] : P.tile_first + blockIdx.x];
@@ -385,11 +417,12 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
         fire = (((H >> p) ^ (H >> q)) & 1u) != 0;
         H2 = H ^ ((1u << p) | (1u << q));
       }
+      const VecT* xn = nullptr;
+      if (fire) fire = u1_neighbour<VecT>(P, P.tile_base[H2], xn);
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (fire) {
         const int slot = n + __popc(m & ((1u << tid) - 1u));
-        const uintptr_t ptr = reinterpret_cast<uintptr_t>(u1_seg_resolve<VecT>(P, P.tile_base[H2]));
-        hh_ptr[slot] = reinterpret_cast<const VecT*>(ptr | ((int)P.hh_q[b] >= P.far_bit ? 1u : 0u));
+        hh_ptr[slot] = reinterpret_cast<const VecT*>(reinterpret_cast<uintptr_t>(xn) | ((int)P.hh_q[b] >= P.far_bit ? 1u : 0u));
         hh_amp[slot] = P.hh_amp[b];
       }
       n += __popc(m);
@@ -397,26 +430,46 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
     if (tid == 0) s_counts[0] = n;
   } else if (tid < 64) {
     const int lane = tid - 32;
-    for (int b = lane; b < P.n_mx; b += 32) {
-      const int q = P.mx_q[b];
-      const uint32_t hbit = (H >> q) & 1u;
-      mx_ptr[b] = reinterpret_cast<const VecT*>(reinterpret_cast<uintptr_t>(u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)])) |
-                                                (q >= P.far_bit ? 1u : 0u));
-      mx_amp[b] = P.mx_amp[b];
-      mx_toff[b] = ((uint32_t)(2 * b + hbit) << k) + lofs;
-    }
-    for (int b = lane; b < P.n_ms; b += 32) {
-      const int q = P.ms_q[b];
-      const uint32_t hbit = (H >> q) & 1u;
-      const VecT* xn = u1_seg_resolve<VecT>(P, P.tile_base[H ^ (1u << q)]);
-      const uint32_t n0 = P.ck1[p_low];                  // rows of this tile whose bit k-1 is clear (they come first)
-      if (hbit == 0) {                                   // rows with bit k-1 set -> first rows of the neighbour (p_low - 1)
-        ms_lo[b] = n0; ms_len[b] = size - n0; ms_ptr[b] = xn - n0;
-      } else {                                           // rows with bit k-1 clear -> last rows of the neighbour (p_low + 1)
-        ms_lo[b] = 0; ms_len[b] = n0; ms_ptr[b] = xn + P.ck1[p_low + 1];
+    int n = 0;
+    for (int b0 = 0; b0 < P.n_mx; b0 += 32) {
+      const int b = b0 + lane;
+      bool on = b < P.n_mx;
+      const VecT* xn = nullptr;
+      int q = 0;
+      if (on) { q = P.mx_q[b]; on = u1_neighbour<VecT>(P, P.tile_base[H ^ (1u << q)], xn); }
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int slot = n + __popc(m & ((1u << lane) - 1u));
+        const uint32_t hbit = (H >> q) & 1u;
+        mx_ptr[slot] = reinterpret_cast<const VecT*>(reinterpret_cast<uintptr_t>(xn) | (q >= P.far_bit ? 1u : 0u));
+        mx_amp[slot] = P.mx_amp[b];
+        mx_toff[slot] = ((uint32_t)(2 * b + hbit) << k) + lofs;
       }
-      ms_amp[b] = P.ms_amp[b];
+      n += __popc(m);
     }
+    if (lane == 0) s_counts[2] = n;
+    n = 0;
+    for (int b0 = 0; b0 < P.n_ms; b0 += 32) {
+      const int b = b0 + lane;
+      bool on = b < P.n_ms;
+      const VecT* xn = nullptr;
+      int q = 0;
+      if (on) { q = P.ms_q[b]; on = u1_neighbour<VecT>(P, P.tile_base[H ^ (1u << q)], xn); }
+      const unsigned m = __ballot_sync(0xffffffffu, on);
+      if (on) {
+        const int slot = n + __popc(m & ((1u << lane) - 1u));
+        const uint32_t hbit = (H >> q) & 1u;
+        const uint32_t n0 = P.ck1[p_low];                  // rows of this tile whose bit k-1 is clear (they come first)
+        if (hbit == 0) {                                   // rows with bit k-1 set -> first rows of the neighbour (p_low - 1)
+          ms_lo[slot] = n0; ms_len[slot] = size - n0; ms_ptr[slot] = xn - n0;
+        } else {                                           // rows with bit k-1 clear -> last rows of the neighbour (p_low + 1)
+          ms_lo[slot] = 0; ms_len[slot] = n0; ms_ptr[slot] = xn + P.ck1[p_low + 1];
+        }
+        ms_amp[slot] = P.ms_amp[b];
+      }
+      n += __popc(m);
+    }
+    if (lane == 0) s_counts[3] = n;
   } else if (tid < 96) {
     const int lane = tid - 64;
     int n = 0;
@@ -444,6 +497,13 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       s_dval[i] = v;
     }
   }
+  if (P.stream_mode == 2) {                             // remote pass: most tiles have nothing to add
+    __syncthreads();
+    if (s_counts[0] + s_counts[2] + s_counts[3] == 0) {
+      if (dot_partials && tid == 0) { dot_partials[2 * blockIdx.x] = 0.0; dot_partials[2 * blockIdx.x + 1] = 0.0; }
+      return;
+    }
+  }
   {
     const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
@@ -454,8 +514,8 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   U1Tile<VecT> T;
   T.xs = xs;
   T.hh_amp = hh_amp; T.hh_ptr = hh_ptr; T.n_hh = s_counts[0];
-  T.mx_amp = mx_amp; T.mx_ptr = mx_ptr; T.mx_toff = mx_toff; T.n_mx = P.n_mx;
-  T.ms_amp = ms_amp; T.ms_ptr = ms_ptr; T.ms_lo = ms_lo; T.ms_len = ms_len; T.n_ms = P.n_ms;
+  T.mx_amp = mx_amp; T.mx_ptr = mx_ptr; T.mx_toff = mx_toff; T.n_mx = s_counts[2];
+  T.ms_amp = ms_amp; T.ms_ptr = ms_ptr; T.ms_lo = ms_lo; T.ms_len = ms_len; T.n_ms = s_counts[3];
   T.mq_coef = mq_coef; T.mq_bit = mq_bit; T.n_mq = s_counts[1];
   T.s_dval = s_dval;
   T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = (int64_t)base;
@@ -950,6 +1010,47 @@ int ed_u1_suggest_rows2(ed_oprep* o, int dtype, int world, int rank, int64_t* lo
   return 2;
 }
 
+// Rows of x outside the given local ranges that the fast kernel reads for the tiles inside them: whole neighbour tiles,
+// merged into ascending disjoint ranges (what the copy engines must bring into the mirror vector before the remote pass).
+void ed_u1_remote_rows(ed_oprep* o, int dtype, int n_ranges, const int64_t* lo, const int64_t* hi, std::vector<int64_t>& out_lo,
+                       std::vector<int64_t>& out_hi) {
+  FastU1Plan* plan = get_plan(o, dtype);
+  ED_REQUIRE(plan->supported, ED_ERR_UNSUPPORTED, "remote rows are defined for the U(1) fast-path kernel only");
+  const int hb = plan->hb;
+  const U1Params& P = plan->P;
+  // host copies of the bond lists
+  std::vector<uint8_t> hh_p(std::max(P.n_hh, 1)), hh_q(std::max(P.n_hh, 1)), mx_q(std::max(P.n_mx, 1)), ms_q(std::max(P.n_ms, 1));
+  plan->hh_p.download(hh_p.data(), hh_p.size()); plan->hh_q.download(hh_q.data(), hh_q.size());
+  plan->mx_q.download(mx_q.data(), mx_q.size()); plan->ms_q.download(ms_q.data(), ms_q.size());
+  const size_t nt = plan->h_base.size();
+  std::vector<uint32_t> tile_H(nt);
+  plan->tile_H.download(tile_H.data(), nt);
+  std::vector<int32_t> index_of((size_t)1 << hb, -1);
+  for (size_t t = 0; t < nt; ++t) index_of[tile_H[t]] = (int32_t)t;
+  auto is_local = [&](size_t t) {
+    const int64_t b = (int64_t)plan->h_base[t];
+    for (int r = 0; r < n_ranges; ++r) if (b >= lo[r] && b < hi[r]) return true;
+    return false;
+  };
+  std::vector<uint8_t> need(nt, 0);
+  for (size_t t = 0; t < nt; ++t) {
+    if (!is_local(t)) continue;
+    const uint32_t H = tile_H[t];
+    auto touch = [&](uint32_t H2) { const int32_t j = index_of[H2]; if (j >= 0 && !is_local((size_t)j)) need[j] = 1; };
+    for (int b = 0; b < P.n_hh; ++b)
+      if (((H >> hh_p[b]) ^ (H >> hh_q[b])) & 1u) touch(H ^ ((1u << hh_p[b]) | (1u << hh_q[b])));
+    for (int b = 0; b < P.n_mx; ++b) touch(H ^ (1u << mx_q[b]));
+    for (int b = 0; b < P.n_ms; ++b) touch(H ^ (1u << ms_q[b]));
+  }
+  out_lo.clear(); out_hi.clear();
+  for (size_t t = 0; t < nt; ++t) {
+    if (!need[t]) continue;
+    const int64_t b = (int64_t)plan->h_base[t], e = b + (int64_t)plan->h_size[t];
+    if (!out_hi.empty() && out_hi.back() == b) out_hi.back() = e;
+    else { out_lo.push_back(b); out_hi.push_back(e); }
+  }
+}
+
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
   (void)side;
   FastU1Plan* plan = get_plan(o, dtype);
@@ -962,6 +1063,14 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   static const int ablate = getenv("EDCUDA_U1_ABLATE") ? atoi(getenv("EDCUDA_U1_ABLATE")) : 0;
   static const int far_bit = getenv("EDCUDA_U1_FARBIT") ? atoi(getenv("EDCUDA_U1_FARBIT")) : -1;   // override of the plan's choice
   if (far_bit >= 0) P.far_bit = far_bit;
+  P.stream_mode = o->x_seg_ptr.empty() ? 0 : o->exchange_mode;
+  P.local_seg_mask = o->local_seg_mask;
+  P.mirror = o->mirror;
+  if (P.stream_mode == 2) {                 // remote pass: neighbour streams only, added to what the local pass wrote
+    ED_REQUIRE(o->mirror != nullptr, ED_ERR_ARGUMENT, "remote pass without a mirror vector (ed_oprep_set_exchange)");
+    P.n_ll = 0;
+    P.accumulate = 1;
+  }
   if (ablate & 1) P.n_ll = 0;
   if (ablate & 2) P.n_hh = 0;
   if (ablate & 4) P.n_mx = 0;

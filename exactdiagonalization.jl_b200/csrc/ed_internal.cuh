@@ -283,6 +283,9 @@ struct ed_oprep {
   int64_t row_lo = 0, row_hi = 0;
   int kernel_choice = 0;
   // x handed over as contiguous segments (multi-GPU: peers' shards mapped over NVLink); empty = plain pointer
+  int exchange_mode = 0;            // 0 one pass through the segments, 1 local pass, 2 remote pass from the mirror
+  uint32_t local_seg_mask = 0;
+  const void* mirror = nullptr;
   std::vector<int64_t> x_seg_lo;
   std::vector<const void*> x_seg_ptr;
   TermsDev terms_left, terms_right;
@@ -305,6 +308,8 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side);                   
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate,
                  double* alpha_dot);
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
+void ed_u1_remote_rows(ed_oprep* o, int dtype, int n_ranges, const int64_t* lo, const int64_t* hi, std::vector<int64_t>& out_lo,
+                       std::vector<int64_t>& out_hi);                                             // apply_u1.cu
 int ed_u1_suggest_rows2(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);   // apply_u1.cu
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
                       double* alpha_dot);

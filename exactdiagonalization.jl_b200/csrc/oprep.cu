@@ -190,6 +190,32 @@ int ed_oprep_suggest_row_ranges(ed_oprep* oprep, int32_t dtype, int32_t world, i
   ED_CATCH
 }
 
+int ed_oprep_remote_rows(ed_oprep* oprep, int32_t dtype, int32_t n_ranges, const int64_t* row_lo, const int64_t* row_hi,
+                         int32_t capacity, int64_t* out_lo, int64_t* out_hi, int32_t* n_out) {
+  ED_TRY
+  ED_REQUIRE(oprep && row_lo && row_hi && n_out && n_ranges >= 1, ED_ERR_ARGUMENT, "bad argument");
+  ED_REQUIRE(!oprep->rbasis && ed_apply_u1_supported(oprep, dtype, ED_SIDE_LEFT), ED_ERR_UNSUPPORTED,
+             "remote rows are defined for the U(1) fast-path kernel only");
+  std::vector<int64_t> lo, hi;
+  ed_u1_remote_rows(oprep, dtype, n_ranges, row_lo, row_hi, lo, hi);
+  *n_out = (int32_t)lo.size();
+  if (out_lo && out_hi) {
+    ED_REQUIRE(capacity >= (int32_t)lo.size(), ED_ERR_ARGUMENT, "output capacity too small (call with NULL outputs to query the count)");
+    for (size_t i = 0; i < lo.size(); ++i) { out_lo[i] = lo[i]; out_hi[i] = hi[i]; }
+  }
+  ED_CATCH
+}
+
+int ed_oprep_set_exchange(ed_oprep* oprep, int32_t mode, const void* mirror, uint32_t local_segment_mask) {
+  ED_TRY
+  ED_REQUIRE(oprep && mode >= 0 && mode <= 2, ED_ERR_ARGUMENT, "bad argument");
+  ED_REQUIRE(mode != 2 || mirror, ED_ERR_ARGUMENT, "the remote pass needs a mirror vector");
+  oprep->exchange_mode = mode;
+  oprep->mirror = mirror;
+  oprep->local_seg_mask = local_segment_mask;
+  ED_CATCH
+}
+
 int ed_oprep_set_x_segments(ed_oprep* oprep, int32_t n_seg, const int64_t* seg_lo, const void* const* seg_ptr) {
   ED_TRY
   ED_REQUIRE(oprep, ED_ERR_ARGUMENT, "null argument");

@@ -98,6 +98,8 @@ SIGNATURES = {
     "ed_oprep_suggest_rows": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64)]),
     "ed_oprep_suggest_row_ranges": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64), P(i32)]),
     "ed_oprep_set_x_segments": (C.c_int, [vp, i32, vp, vp]),
+    "ed_oprep_set_exchange": (C.c_int, [vp, i32, vp, C.c_uint32]),
+    "ed_oprep_remote_rows": (C.c_int, [vp, i32, i32, P(i64), P(i64), i32, P(i64), P(i64), P(i32)]),
     "ed_oprep_set_kernel": (C.c_int, [vp, i32]),
     "ed_apply": (C.c_int, [vp, vp, i64, vp, i64, i32, i32, i32]),
     "ed_apply_async": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),

@@ -182,7 +182,10 @@ class P2PShardedMatvec:
     shared buffers are kept so that a Lanczos loop can ping-pong between them.  Only the U(1) fast-path kernel consumes
     segmented inputs."""
 
-    def __init__(self, opr, rank: int, world: int, dtype=None, group=None, n_buffers: int = 2):
+    def __init__(self, opr, rank: int, world: int, dtype=None, group=None, n_buffers: int = 2, exchange: str = "p2p"):
+        """exchange = "p2p": the kernel loads peer tiles itself over NVLink; "dma": split exchange -- copy engines pull the
+        needed peer rows into a local mirror vector while a first kernel pass does everything that is rank-local, a
+        second pass adds the contributions of the mirrored rows (ed_oprep_set_exchange / ed_oprep_remote_rows)."""
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -192,6 +195,7 @@ class P2PShardedMatvec:
         self.t_dtype = torch.complex128 if self.np_dtype == np.complex128 else torch.float64
         self.code = ED_C128 if self.np_dtype == np.complex128 else ED_F64
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.dma = exchange == "dma"
         self.rank_ranges = []          # per rank: its 1 or 2 (lo, hi) row ranges
         for r in range(world):
             lo, hi, n = (C.c_int64 * 2)(), (C.c_int64 * 2)(), C.c_int32()
@@ -242,7 +246,41 @@ class P2PShardedMatvec:
         self.seg_lo = (C.c_int64 * (self.n_seg + 1))(*([s_[0] for s_ in segs] + [self.dim]))
         self.seg_ptr = [[base_ptr[b][r] + o for (_, r, o) in segs] for b in range(n_buffers)]
         self._token = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        self._dot_tmp = torch.zeros(2, 2, dtype=torch.float64, device=self.dev)
+        self._dot_tmp = torch.zeros(4, 2, dtype=torch.float64, device=self.dev)
+        self.local_seg_mask = sum(1 << i for i, (_, r, _) in enumerate(segs) if r == rank)
+        if self.dma:
+            self._setup_dma(segs, base_ptr, n_buffers)
+
+    def _setup_dma(self, segs, base_ptr, n_buffers):
+        """Mirror vector + the list of peer copies that fill the rows the local tiles read from other ranks."""
+        torch = self.torch
+        nr = len(self.local_ranges)
+        lo = (C.c_int64 * nr)(*[r[0] for r in self.local_ranges])
+        hi = (C.c_int64 * nr)(*[r[1] for r in self.local_ranges])
+        n = C.c_int32()
+        check(lib.ed_oprep_remote_rows(self.opr._handle, self.code, nr, lo, hi, 0, None, None, C.byref(n)))
+        out_lo, out_hi = (C.c_int64 * max(n.value, 1))(), (C.c_int64 * max(n.value, 1))()
+        check(lib.ed_oprep_remote_rows(self.opr._handle, self.code, nr, lo, hi, n.value, out_lo, out_hi, C.byref(n)))
+        self.mirror = torch.empty(self.dim, dtype=self.t_dtype, device=self.dev)
+        item = self.np_dtype.itemsize
+        seg_hi = [s_[0] for s_ in segs[1:]] + [self.dim]
+        rows = [sum(h - l for l, h in rr) for rr in self.rank_ranges]
+
+        class _Peer:          # torch view of a peer rank's whole local vector (IPC-mapped pointer)
+            def __init__(self, ptr, n_, typestr):
+                self.__cuda_array_interface__ = {"shape": (n_,), "typestr": typestr, "data": (ptr, False), "version": 2, "strides": None}
+
+        self._peer_views = [[torch.as_tensor(_Peer(base_ptr[b][r], max(rows[r], 1), self.np_dtype.str), device=self.dev)
+                             for r in range(self.world)] for b in range(n_buffers)]
+        self.copies = []       # (mirror start, rank, start inside that rank's vector, length)
+        for a, b_ in zip(list(out_lo)[: n.value], list(out_hi)[: n.value]):
+            for (s_lo, r, off_bytes), s_hi in zip(segs, seg_hi):
+                c0, c1 = max(a, s_lo), min(b_, s_hi)
+                if c1 > c0:
+                    assert r != self.rank
+                    self.copies.append((c0, r, off_bytes // item + (c0 - s_lo), c1 - c0))
+        self.remote_rows = sum(c[3] for c in self.copies)
+        self._copy_streams = [torch.cuda.Stream(device=self.dev) for _ in range(4)]
 
     def x_buffer(self, which: int = 0):
         """This rank's rows of shared input buffer `which` (a torch tensor; write x here; layout = local_ranges)."""
@@ -253,27 +291,55 @@ class P2PShardedMatvec:
         if self.world > 1:
             self.dist.all_reduce(self._token, group=self.group)
 
+    def _apply_ranges(self, y_local, dots):
+        """one ed_apply_async per local row range; dots: list of (2,) tensors or None"""
+        for i, (lo, hi, off) in enumerate(self.local_ranges):
+            dot = None if dots is None else dots[i]
+            if hi <= lo:
+                if dot is not None:
+                    dot.zero_()
+                continue
+            self.opr.set_rows(lo, hi)
+            check(lib.ed_apply_async(self.opr._handle, y_local[off:].data_ptr(), None, self.code, ED_SIDE_LEFT, 0,
+                                     dot.data_ptr() if dot is not None else None))
+
     def matvec(self, y_local, which: int = 0, dot_out=None):
         torch = self.torch
         ptrs = (C.c_void_p * self.n_seg)(*self.seg_ptr[which])
+        nr = len(self.local_ranges)
+        main = torch.cuda.current_stream()
         check(lib.ed_oprep_set_x_segments(self.opr._handle, self.n_seg, self.seg_lo, ptrs))
-        check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
-        two = len(self.local_ranges) > 1
+        check(lib.ed_set_stream(C.c_void_p(main.cuda_stream), 1))
+        n_dots = nr
         try:
-            for i, (lo, hi, off) in enumerate(self.local_ranges):
-                self.opr.set_rows(lo, hi)
-                dot = None if dot_out is None else (self._dot_tmp[i] if two else dot_out)
-                if hi <= lo:
-                    if dot is not None:
-                        dot.zero_()
-                    continue
-                check(lib.ed_apply_async(self.opr._handle, y_local[off:].data_ptr(), None, self.code, ED_SIDE_LEFT, 0,
-                                         dot.data_ptr() if dot is not None else None))
+            if not self.dma:
+                self._apply_ranges(y_local, None if dot_out is None else [self._dot_tmp[i] for i in range(nr)])
+            else:
+                ready = torch.cuda.Event()
+                ready.record(main)                      # x is written and fenced at this point of the stream
+                check(lib.ed_oprep_set_exchange(self.opr._handle, 1, None, self.local_seg_mask))
+                self._apply_ranges(y_local, None if dot_out is None else [self._dot_tmp[i] for i in range(nr)])
+                used = set()
+                for i, (m0, r, s0, ln) in enumerate(self.copies):   # copy engines, concurrent with the local pass
+                    st = self._copy_streams[i % len(self._copy_streams)]
+                    if i % len(self._copy_streams) not in used:
+                        st.wait_event(ready)
+                        used.add(i % len(self._copy_streams))
+                    with torch.cuda.stream(st):
+                        self.mirror[m0:m0 + ln].copy_(self._peer_views[which][r][s0:s0 + ln], non_blocking=True)
+                for j in used:
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_streams[j])
+                    main.wait_event(ev)
+                check(lib.ed_oprep_set_exchange(self.opr._handle, 2, C.c_void_p(self.mirror.data_ptr()), self.local_seg_mask))
+                self._apply_ranges(y_local, None if dot_out is None else [self._dot_tmp[nr + i] for i in range(nr)])
+                n_dots = 2 * nr
         finally:
+            lib.ed_oprep_set_exchange(self.opr._handle, 0, None, 0)
             lib.ed_set_stream(None, 0)
             lib.ed_oprep_set_x_segments(self.opr._handle, 0, None, None)
-        if two and dot_out is not None:
-            torch.add(self._dot_tmp[0], self._dot_tmp[1], out=dot_out)
+        if dot_out is not None:
+            torch.sum(self._dot_tmp[:n_dots], dim=0, out=dot_out)
         return y_local
 
     def close(self):
@@ -291,8 +357,8 @@ class ShardedLanczos:
 
     def __init__(self, opr, rank: int = 0, world: int = 1, dtype=None, group=None, exchange: str = "allgather"):
         """exchange = "allgather" (NCCL all-gather of x per step) or "p2p" (peer loads of the far tiles, no gather)."""
-        self.p2p = exchange == "p2p"
-        self.mv = P2PShardedMatvec(opr, rank, world, dtype, group) if self.p2p else ShardedMatvec(opr, rank, world, dtype, group)
+        self.p2p = exchange in ("p2p", "dma")
+        self.mv = P2PShardedMatvec(opr, rank, world, dtype, group, exchange=exchange) if self.p2p else ShardedMatvec(opr, rank, world, dtype, group)
         torch = self.mv.torch
         n = self.mv.n_local
         self.n_local = n

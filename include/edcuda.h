@@ -192,6 +192,16 @@ int ed_oprep_suggest_rows(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t
  * its threads split rows with splitrange, src/util.jl:102-121). */
 int ed_oprep_suggest_row_ranges(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi,
                                 int32_t* n_ranges);
+/* Split exchange for segmented inputs.  mode 1 (local pass): neighbour tiles that live in a segment outside
+ * local_segment_mask (bit s = segment s is this process's own memory) are skipped; mode 2 (remote pass): only those
+ * tiles are read -- from `mirror`, a full-length local vector into which the caller copied the rows listed by
+ * ed_oprep_remote_rows (copy engines over NVLink, concurrently with the local pass) -- and added to `out`; with a dot
+ * pointer each pass returns its own part of <x, Hx>.  mode 0 (default): one pass, peers read through the segments. */
+int ed_oprep_set_exchange(ed_oprep* oprep, int32_t mode, const void* mirror, uint32_t local_segment_mask);
+/* Rows of x outside the row ranges [row_lo[i], row_hi[i]) that the fast kernel reads when it applies those ranges
+ * (whole neighbour tiles, ascending, merged).  Two-call protocol: out_lo = out_hi = NULL returns the count in *n_out. */
+int ed_oprep_remote_rows(ed_oprep* oprep, int32_t dtype, int32_t n_ranges, const int64_t* row_lo, const int64_t* row_hi,
+                         int32_t capacity, int64_t* out_lo, int64_t* out_hi, int32_t* n_out);
 /* Hand the input vector over as n_seg (<= 16) contiguous segments instead of one pointer: segment s holds rows
  * [seg_lo[s], seg_lo[s+1]) at device address seg_ptr[s] (local memory or a peer GPU's buffer opened with
  * ed_ipc_open_handle).  While set, ed_apply_async ignores its `x` argument.  n_seg = 0 clears.  Only the U(1)

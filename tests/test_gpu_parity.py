@@ -799,6 +799,91 @@ def test_fast_path_segmented_input_single_gpu(gpu_ed, n, n_dn, model):
     assert rel_err(np.concatenate(outs), exp) < TOL
     assert abs(sum(dots) - float(np.dot(x, exp))) < 1e-10 * np.linalg.norm(x) * np.linalg.norm(exp)
 
+@pytest.mark.parametrize("n,n_dn,model,world", [(20, 10, "xxz", 2), (22, 11, "xxz", 4), (20, 7, "j1j2", 3), (18, 9, "open", 2)])
+def test_wrap_aware_row_ranges_single_gpu(gpu_ed, n, n_dn, model, world):
+    """ed_oprep_suggest_row_ranges on one device: for a ring every "rank" gets two tile-aligned ranges (same high bits in
+    both halves of the basis) that tile the basis exactly and keep the wrapping bond local; an open chain gets the plain
+    single range.  x is handed over as the corresponding segments; the assembled result equals the oracle's."""
+    ed = gpu_ed
+    import ctypes as C
+    import torch
+    from edcuda._lib import lib, check
+    hs, _ = ed.spin_half_system(n)
+    if model == "xxz":
+        h = ed.models.xxz_bonds(hs, ed.lattices.chain_bonds(n), 1.0, 0.37)
+    elif model == "open":
+        h = ed.models.xxz_bonds(hs, ed.lattices.chain_bonds(n, 1, periodic=False), 0.8, -1.1)
+    else:
+        h = ed.simplify(ed.models.heisenberg_bonds(hs, ed.lattices.chain_bonds(n, 1)) + ed.models.heisenberg_bonds(hs, ed.lattices.chain_bonds(n, 2), 0.5))
+    hsr = ed.represent(ed.HilbertSpaceSector(hs, n - 2 * n_dn))
+    d = hsr.dimension
+    x = np.random.default_rng(n + world).standard_normal(d)
+    _, exp = _c_oracle_apply(n, n_dn, h, x)
+    xt = torch.from_numpy(x).cuda()
+    opr = ed.represent(hsr, h)
+    rank_ranges = []
+    for r in range(world):
+        lo, hi, nr = (C.c_int64 * 2)(), (C.c_int64 * 2)(), C.c_int32()
+        check(lib.ed_oprep_suggest_row_ranges(opr._handle, ed.ED_F64, world, r, lo, hi, C.byref(nr)))
+        assert nr.value == (1 if model == "open" else 2)
+        rank_ranges.append([(lo[i], hi[i]) for i in range(nr.value)])
+    flat = sorted((lo, hi, r) for r, rr in enumerate(rank_ranges) for lo, hi in rr if hi > lo)
+    assert flat[0][0] == 0 and flat[-1][1] == d and all(a[1] == b[0] for a, b in zip(flat[:-1], flat[1:]))   # exact tiling
+    rows = [sum(hi - lo for lo, hi in rr) for rr in rank_ranges]
+    assert max(rows) - min(rows) <= 0.2 * d / world + 4096                                                   # balanced
+    bufs = [xt[lo:hi].clone() for lo, hi, _ in flat]
+    seg_lo = (C.c_int64 * (len(flat) + 1))(*([f[0] for f in flat] + [d]))
+    ptrs = (C.c_void_p * len(flat))(*[t.data_ptr() for t in bufs])
+    y = np.zeros(d)
+    dot_total = 0.0
+    for rr in rank_ranges:
+        for lo, hi in rr:
+            if hi <= lo:
+                continue
+            o_r = ed.represent(hsr, h).set_rows(lo, hi)
+            check(lib.ed_oprep_set_x_segments(o_r._handle, len(flat), seg_lo, ptrs))
+            y_r = torch.zeros(hi - lo, dtype=torch.float64, device="cuda")
+            dot = torch.zeros(2, dtype=torch.float64, device="cuda")
+            check(lib.ed_apply_async(o_r._handle, y_r.data_ptr(), None, ed.ED_F64, 0, 0, dot.data_ptr()))
+            torch.cuda.synchronize()
+            y[lo:hi] = y_r.cpu().numpy()
+            dot_total += float(dot[0])
+    assert rel_err(y, exp) < TOL
+    assert abs(dot_total - float(np.dot(x, exp))) < 1e-10 * np.linalg.norm(x) * np.linalg.norm(exp)
+    # split exchange: a local pass that skips every tile living in another rank's segment, then a remote pass that reads
+    # exactly the rows ed_oprep_remote_rows lists from a mirror vector (everything else in the mirror is NaN)
+    y2 = np.zeros(d)
+    dot_total = 0.0
+    for r, rr in enumerate(rank_ranges):
+        mask = sum(1 << i for i, f in enumerate(flat) if f[2] == r)
+        nr = len(rr)
+        lo_a, hi_a = (C.c_int64 * nr)(*[a for a, _ in rr]), (C.c_int64 * nr)(*[b for _, b in rr])
+        cnt = C.c_int32()
+        o_q = ed.represent(hsr, h)
+        check(lib.ed_oprep_remote_rows(o_q._handle, ed.ED_F64, nr, lo_a, hi_a, 0, None, None, C.byref(cnt)))
+        rl, rh = (C.c_int64 * max(cnt.value, 1))(), (C.c_int64 * max(cnt.value, 1))()
+        check(lib.ed_oprep_remote_rows(o_q._handle, ed.ED_F64, nr, lo_a, hi_a, cnt.value, rl, rh, C.byref(cnt)))
+        mirror = torch.full((d,), float("nan"), dtype=torch.float64, device="cuda")
+        for a, b in zip(list(rl)[: cnt.value], list(rh)[: cnt.value]):
+            assert not any(lo <= a < hi for lo, hi in rr)          # remote rows are outside the rank's own ranges
+            mirror[a:b] = xt[a:b]
+        for lo, hi in rr:
+            if hi <= lo:
+                continue
+            o_r = ed.represent(hsr, h).set_rows(lo, hi)
+            check(lib.ed_oprep_set_x_segments(o_r._handle, len(flat), seg_lo, ptrs))
+            y_r = torch.zeros(hi - lo, dtype=torch.float64, device="cuda")
+            dots = torch.zeros(2, 2, dtype=torch.float64, device="cuda")
+            check(lib.ed_oprep_set_exchange(o_r._handle, 1, None, mask))
+            check(lib.ed_apply_async(o_r._handle, y_r.data_ptr(), None, ed.ED_F64, 0, 0, dots[0].data_ptr()))
+            check(lib.ed_oprep_set_exchange(o_r._handle, 2, C.c_void_p(mirror.data_ptr()), mask))
+            check(lib.ed_apply_async(o_r._handle, y_r.data_ptr(), None, ed.ED_F64, 0, 0, dots[1].data_ptr()))
+            torch.cuda.synchronize()
+            y2[lo:hi] = y_r.cpu().numpy()
+            dot_total += float(dots[:, 0].sum())
+    assert np.all(np.isfinite(y2)) and rel_err(y2, exp) < TOL
+    assert abs(dot_total - float(np.dot(x, exp))) < 1e-10 * np.linalg.norm(x) * np.linalg.norm(exp)
+
 def test_fast_path_falls_back_for_unsupported_operators(gpu_ed):
     ed = gpu_ed
     n = 10
@@ -890,6 +975,22 @@ def _nccl_worker(rank, world, port, q):
     dist.all_gather_object(parts, [(lo, yp[off:off + hi - lo].cpu().numpy()) for lo, hi, off in pm.local_ranges])
     yps = [a for _, a in sorted([p for pr in parts for p in pr], key=lambda t: t[0])]
     pm.close()
+    # split exchange (copy engines fill a mirror vector during the local pass) must give the same rows and the same dot
+    pd = P2PShardedMatvec(ed.represent(hsr, h), rank, world, n_buffers=1, exchange="dma")
+    xd = pd.x_buffer(0)
+    for lo, hi, off in pd.local_ranges:
+        xd[off:off + hi - lo].copy_(torch.arange(lo, hi, dtype=torch.float64, device="cuda").sin())
+    yd = torch.zeros_like(xd)
+    dotd = torch.zeros(2, dtype=torch.float64, device="cuda")
+    pd.fence()
+    pd.matvec(yd, 0, dotd)
+    torch.cuda.synchronize()
+    assert pd.remote_rows > 0
+    assert float((yd - yp).abs().max()) <= 1e-12 * float(yp.abs().max())
+    assert abs(float(dotd[0]) - float(dotp[0])) < 1e-9 * float(xp.norm() * yp.norm())
+    pd.close()
+    res_d = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="dma").run(120, seed=4)
+    assert abs(res_d.ritz[0] - res_p.ritz[0]) < 1e-10
     mv = ShardedMatvec(ed.represent(hsr, h), rank, world)
     x = torch.arange(mv.lo, mv.hi, dtype=torch.float64, device="cuda").sin()
     y = torch.zeros_like(x)

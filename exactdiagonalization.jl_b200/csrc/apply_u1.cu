@@ -185,12 +185,43 @@ struct U1Tile {
   int p_low;
   int64_t base;
   double d_tile;
+  uint32_t bar;        // shared-memory address of the mbarrier the bulk copy of the x tile completes on (TMA staging)
 };
+
+// ---- TMA (bulk async copy) staging of the x tile ---------------------------------------------------------
+// One thread arms an mbarrier with the byte count and issues ONE cp.async.bulk global -> shared for the 16-byte
+// aligned middle of the tile; the copy runs on the TMA unit while the CTA builds its bond lists and consumes the
+// neighbour streams (which do not need the tile), and every thread waits on the barrier right before its first
+// shared-memory read.  No LSU instructions, no registers, no st.shared for the staging.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the init visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
 
 // Slab body.  Slab r holds rows i = tid + r*THREADS.  NF = number of COMPLETE slabs of this tile (compile time:
 // constant offsets, no predicates, NF+1 independent loads in flight per thread and bond).  The last, partial slab is
 // addressed through the clamped per-thread index `it`, so every load stays in bounds; only its store is predicated.
-template <typename VecT, int THREADS, int NF>
+template <typename VecT, int THREADS, int NF, bool TMA>
 __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<VecT>& T,
                                              VecT* __restrict__ y, bool want_dot, double& dre, double& dim_, int slab0) {
   constexpr int CH = sizeof(VecT) == 8 ? 6 : 3;   // loads issued back to back before their FMAs (register budget)
@@ -201,9 +232,12 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
   const bool tail_ok = i_tail < size;
   const uint32_t it = tail_ok ? i_tail : size - 1;
   VecT acc[NF > 0 ? NF : 1];
-  VecT acc_t;
-  // diagonal
-  {
+  VecT acc_t = vzero((VecT*)nullptr);
+#pragma unroll
+  for (int r = 0; r < NF; ++r) acc[r] = vzero((VecT*)nullptr);
+
+  // diagonal (reads the x tile in shared memory)
+  auto part_diag = [&]() {
     const uint8_t* dc = P.dcode + T.lofs;
     const double* dl = P.dlow + T.lofs;
     double dd[NF > 0 ? NF : 1];
@@ -238,107 +272,134 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
         if (r < NF) dd[r] += d; else dt += d;
       }
     }
+    // the accumulators are still zero on the default path (fma(d, x, 0) == d * x exactly)
 #pragma unroll
-    for (int r = 0; r < NF; ++r) acc[r] = vec_scale<VecT>(dd[r], xs[tid + r * THREADS]);
-    acc_t = vec_scale<VecT>(dt, xs[it]);
-  }
+    for (int r = 0; r < NF; ++r) vec_fma(acc[r], dd[r], xs[tid + r * THREADS]);
+    vec_fma(acc_t, dt, xs[it]);
+  };
   // bonds inside the high bits: same local index in another tile -> coalesced streams
+  auto part_high = [&]() {
 #pragma unroll 1
-  for (int e = 0; e < T.n_hh; ++e) {
-    const double a = T.hh_amp[e];
-    const uintptr_t tagged = reinterpret_cast<uintptr_t>(T.hh_ptr[e]);
-    const bool far = tagged & 1u;                        // warp-uniform: one-shot read of a far tile
-    const VecT* xe = reinterpret_cast<const VecT*>(tagged & ~(uintptr_t)1u);
-    const VecT* xt = xe + tid;
-    const uint64_t pol = l2_policy(far ? 1 : 0);
-    const VecT vt = ld_hint(xe + it, pol);
+    for (int e = 0; e < T.n_hh; ++e) {
+      const double a = T.hh_amp[e];
+      const uintptr_t tagged = reinterpret_cast<uintptr_t>(T.hh_ptr[e]);
+      const bool far = tagged & 1u;                        // warp-uniform: one-shot read of a far tile
+      const VecT* xe = reinterpret_cast<const VecT*>(tagged & ~(uintptr_t)1u);
+      const VecT* xt = xe + tid;
+      const uint64_t pol = l2_policy(far ? 1 : 0);
+      const VecT vt = ld_hint(xe + it, pol);
 #pragma unroll
-    for (int r0 = 0; r0 < NF; r0 += CH) {
-      VecT v[CH];
+      for (int r0 = 0; r0 < NF; r0 += CH) {
+        VecT v[CH];
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) v[c] = ld_hint(xt + (r0 + c) * THREADS, pol);
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) v[c] = ld_hint(xt + (r0 + c) * THREADS, pol);
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+      }
+      vec_fma(acc_t, a, vt);
     }
-    vec_fma(acc_t, a, vt);
-  }
+  };
   // straddling bonds on bit k-1: a contiguous block of rows reads a shifted stream of the neighbour tile
+  auto part_block = [&]() {
 #pragma unroll 1
-  for (int e = 0; e < T.n_ms; ++e) {
-    const double a = T.ms_amp[e];
-    const VecT* xe = T.ms_ptr[e];            // already offset: column = row index
-    const uint32_t lo = T.ms_lo[e], len = T.ms_len[e];
-    const VecT* xt = xe + tid;
-    const VecT vt = (it - lo < len) ? ldg_val(xe + it) : vzero((VecT*)nullptr);
+    for (int e = 0; e < T.n_ms; ++e) {
+      const double a = T.ms_amp[e];
+      const VecT* xe = T.ms_ptr[e];            // already offset: column = row index
+      const uint32_t lo = T.ms_lo[e], len = T.ms_len[e];
+      const VecT* xt = xe + tid;
+      const VecT vt = (it - lo < len) ? ldg_val(xe + it) : vzero((VecT*)nullptr);
 #pragma unroll
-    for (int r0 = 0; r0 < NF; r0 += CH) {
-      VecT v[CH];
+      for (int r0 = 0; r0 < NF; r0 += CH) {
+        VecT v[CH];
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) v[c] = ((uint32_t)(tid + (r0 + c) * THREADS) - lo < len) ? ldg_val(xt + (r0 + c) * THREADS) : vzero((VecT*)nullptr);
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) v[c] = ((uint32_t)(tid + (r0 + c) * THREADS) - lo < len) ? ldg_val(xt + (r0 + c) * THREADS) : vzero((VecT*)nullptr);
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
+      }
+      vec_fma(acc_t, a, vt);
     }
-    vec_fma(acc_t, a, vt);
-  }
+  };
   // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers
+  auto part_low = [&]() {
 #pragma unroll 1
-  for (int c = 0; c < P.n_ll; ++c) {
-    const uint8_t* cnt = P.ell_cnt[c] + T.gofs;
-    int nmax = (int)__ldg(cnt + (it >> 5));
+    for (int c = 0; c < P.n_ll; ++c) {
+      const uint8_t* cnt = P.ell_cnt[c] + T.gofs;
+      int nmax = (int)__ldg(cnt + (it >> 5));
 #pragma unroll
-    for (int r = 0; r < NF; ++r) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // warp-uniform
-    const uint32_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
-    const double a = P.ll_amp[c];
+      for (int r = 0; r < NF; ++r) nmax = max(nmax, (int)__ldg(cnt + ((tid + r * THREADS) >> 5)));   // warp-uniform
+      const uint32_t* e = P.ell[c] + P.ell_ofs[c * (P.k + 1) + T.p_low];
+      const double a = P.ll_amp[c];
 #pragma unroll 1
-    for (int sl = 0; sl < nmax; ++sl) {     // one iteration = a PAIR of slots packed in one 32-bit word
-      const uint32_t* et = e + tid;
-      const uint32_t jt = __ldg(e + it);
+      for (int sl = 0; sl < nmax; ++sl) {     // one iteration = a PAIR of slots packed in one 32-bit word
+        const uint32_t* et = e + tid;
+        const uint32_t jt = __ldg(e + it);
+#pragma unroll
+        for (int r0 = 0; r0 < NF; r0 += CH) {
+          uint32_t j[CH];
+#pragma unroll
+          for (int cc = 0; cc < CH; ++cc)
+            if (r0 + cc < NF) j[cc] = __ldg(et + (r0 + cc) * THREADS);
+#pragma unroll
+          for (int cc = 0; cc < CH; ++cc)
+            if (r0 + cc < NF) { vec_fma(acc[r0 + cc], a, xs[j[cc] & 0xFFFFu]); vec_fma(acc[r0 + cc], a, xs[j[cc] >> 16]); }
+        }
+        vec_fma(acc_t, a, xs[jt & 0xFFFFu]);
+        vec_fma(acc_t, a, xs[jt >> 16]);
+        e += size;
+      }
+    }
+  };
+  // bonds straddling bit k: tabulated local column inside the neighbouring tile (0xFFFF = does not fire)
+  auto part_straddle = [&]() {
+#pragma unroll 1
+    for (int e = 0; e < T.n_mx; ++e) {
+      const uint16_t* tab = P.mx_tab + T.mx_toff[e];
+      const uint16_t* tt = tab + tid;
+      const uintptr_t tagged = reinterpret_cast<uintptr_t>(T.mx_ptr[e]);
+      const VecT* xe = reinterpret_cast<const VecT*>(tagged & ~(uintptr_t)1u);
+      const uint64_t pol = l2_policy((tagged & 1u) ? 1 : 0);
+      const double a = T.mx_amp[e];
+      const uint32_t jt = __ldg(tab + it);
+      const VecT vt = jt != 0xFFFFu ? ld_hint(xe + jt, pol) : vzero((VecT*)nullptr);
 #pragma unroll
       for (int r0 = 0; r0 < NF; r0 += CH) {
         uint32_t j[CH];
+        VecT v[CH];
 #pragma unroll
-        for (int cc = 0; cc < CH; ++cc)
-          if (r0 + cc < NF) j[cc] = __ldg(et + (r0 + cc) * THREADS);
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) j[c] = __ldg(tt + (r0 + c) * THREADS);
 #pragma unroll
-        for (int cc = 0; cc < CH; ++cc)
-          if (r0 + cc < NF) { vec_fma(acc[r0 + cc], a, xs[j[cc] & 0xFFFFu]); vec_fma(acc[r0 + cc], a, xs[j[cc] >> 16]); }
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) v[c] = j[c] != 0xFFFFu ? ld_hint(xe + j[c], pol) : vzero((VecT*)nullptr);
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
       }
-      vec_fma(acc_t, a, xs[jt & 0xFFFFu]);
-      vec_fma(acc_t, a, xs[jt >> 16]);
-      e += size;
+      vec_fma(acc_t, a, vt);
     }
+  };
+
+  if (TMA) {
+    // everything that reads other tiles first (global loads in flight while the bulk copy of this tile lands),
+    // then wait for the tile and do the shared-memory parts
+    part_high();
+    part_block();
+    part_straddle();
+    mbar_wait(T.bar, 0);                     // completed once per CTA: later passes see the finished phase at once
+    part_diag();
+    part_low();
+  } else {
+    part_diag();
+    part_high();
+    part_block();
+    part_low();
+    part_straddle();
   }
-  // bonds straddling bit k: tabulated local column inside the neighbouring tile (0xFFFF = does not fire)
-#pragma unroll 1
-  for (int e = 0; e < T.n_mx; ++e) {
-    const uint16_t* tab = P.mx_tab + T.mx_toff[e];
-    const uint16_t* tt = tab + tid;
-    const uintptr_t tagged = reinterpret_cast<uintptr_t>(T.mx_ptr[e]);
-    const VecT* xe = reinterpret_cast<const VecT*>(tagged & ~(uintptr_t)1u);
-    const uint64_t pol = l2_policy((tagged & 1u) ? 1 : 0);
-    const double a = T.mx_amp[e];
-    const uint32_t jt = __ldg(tab + it);
-    const VecT vt = jt != 0xFFFFu ? ld_hint(xe + jt, pol) : vzero((VecT*)nullptr);
-#pragma unroll
-    for (int r0 = 0; r0 < NF; r0 += CH) {
-      uint32_t j[CH];
-      VecT v[CH];
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) j[c] = __ldg(tt + (r0 + c) * THREADS);
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) v[c] = j[c] != 0xFFFFu ? ld_hint(xe + j[c], pol) : vzero((VecT*)nullptr);
-#pragma unroll
-      for (int c = 0; c < CH; ++c)
-        if (r0 + c < NF) vec_fma(acc[r0 + c], a, v[c]);
-    }
-    vec_fma(acc_t, a, vt);
-  }
+
   // store (row-owner writes)
   const int64_t row0 = (int64_t)T.base + tid;
   VecT* yt = y + (row0 - P.row_lo);
@@ -364,26 +425,29 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
   }
 }
 
-template <typename VecT, int THREADS, int R, int NF>
+template <typename VecT, int THREADS, int R, int NF, bool TMA>
 struct U1Dispatch {
   static __device__ __forceinline__ void run(int nfull, const U1Params& P, const U1Tile<VecT>& T, VecT* y,
                                              bool want_dot, double& dre, double& dim_, int slab0) {
-    if (nfull == NF) u1_tile_body<VecT, THREADS, NF>(P, T, y, want_dot, dre, dim_, slab0);
-    else U1Dispatch<VecT, THREADS, R, NF - 1>::run(nfull, P, T, y, want_dot, dre, dim_, slab0);
+    if (nfull == NF) u1_tile_body<VecT, THREADS, NF, TMA>(P, T, y, want_dot, dre, dim_, slab0);
+    else U1Dispatch<VecT, THREADS, R, NF - 1, TMA>::run(nfull, P, T, y, want_dot, dre, dim_, slab0);
   }
 };
-template <typename VecT, int THREADS, int R>
-struct U1Dispatch<VecT, THREADS, R, -1> {
+template <typename VecT, int THREADS, int R, bool TMA>
+struct U1Dispatch<VecT, THREADS, R, -1, TMA> {
   static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT>&, VecT*, bool, double&, double&, int) {}
 };
 
 // One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
-template <typename VecT, int THREADS, int R>
+// TMA = true: the x tile is staged by one bulk async copy (see tma_load_1d) instead of the load/st.shared loop.
+template <typename VecT, int THREADS, int R, bool TMA>
 __global__ void __launch_bounds__(THREADS, (R <= 7 && sizeof(VecT) == 8) ? 3 : 2)
 k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
-  double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 1);
+  // tile_cap + 2 elements: the tile, the zero the ELL padding points at, and one element of slack so that the tile can
+  // start at an odd element (TMA staging keeps the 16-byte phase of the global address)
+  VecT* xs = reinterpret_cast<VecT*>(smem_raw);
+  double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 2);
   double* mx_amp = hh_amp + U1_MAX_HH;
   double* mq_coef = mx_amp + U1_MAX_MX;
   double* s_dval = mq_coef + U1_MAX_MQ;                                // 256
@@ -396,6 +460,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   double* ms_amp = reinterpret_cast<double*>(ms_len + U1_MAX_MS);
   const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + U1_MAX_MS);
   __shared__ int s_counts[4];
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
   const uint32_t H = P.tile_H[P.tile_order ? P.tile_order[blockIdx.x] : P.tile_first + blockIdx.x];
@@ -404,6 +469,22 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
   const uint64_t base = P.tile_base[H];
   const int k = P.k;
+
+  // ---- x tile: bulk async copy issued before anything else (TMA staging) ------------------------------------
+  // The copy needs 16-byte aligned addresses and sizes: xs keeps the phase of the global address (xs = smem + head
+  // elements), the aligned middle goes through the TMA unit, an odd first / last element through plain loads.
+  const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
+  uint32_t tma_bytes = 0, tma_head = 0;
+  if (TMA) {
+    tma_head = (uint32_t)((reinterpret_cast<uintptr_t>(xo) & 15u) / sizeof(VecT));   // 0, or 1 for an odd double
+    if (sizeof(VecT) == 8) xs += tma_head;
+    if (size > tma_head) tma_bytes = (uint32_t)(((size - tma_head) * sizeof(VecT)) & ~(size_t)15);
+    if (tid == 96) {
+      mbar_init(smem_addr(&s_bar), 1);
+      if (tma_bytes) tma_load_1d(smem_addr(xs + tma_head), xo + tma_head, tma_bytes, smem_addr(&s_bar));
+      else mbar_arrive(smem_addr(&s_bar));              // nothing to copy: complete the phase so that waits fall through
+    }
+  }
 
   // ---- prologue: per-tile bond lists (deterministic ballot compaction), x tile --------------------------
   if (tid < 32) {
@@ -500,12 +581,19 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   if (P.stream_mode == 2) {                             // remote pass: most tiles have nothing to add
     __syncthreads();
     if (s_counts[0] + s_counts[2] + s_counts[3] == 0) {
+      if (TMA) mbar_wait(smem_addr(&s_bar), 0);               // never leave the CTA with a bulk copy in flight
       if (dot_partials && tid == 0) { dot_partials[2 * blockIdx.x] = 0.0; dot_partials[2 * blockIdx.x + 1] = 0.0; }
       return;
     }
   }
-  {
-    const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
+  if (TMA) {
+    // elements the bulk copy does not cover (at most one at either end; the whole tile when it is tiny)
+    const uint32_t done_hi = tma_head + (uint32_t)(tma_bytes / sizeof(VecT));
+    if (tid >= 128) {
+      for (uint32_t i = tid - 128; i < size; i += THREADS - 128)
+        if (i < tma_head || i >= done_hi) xs[i] = ldg_val(xo + i);
+    }
+  } else {
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
   }
   if (tid == 0) xs[size] = vzero((VecT*)nullptr);
@@ -520,13 +608,14 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   T.s_dval = s_dval;
   T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = (int64_t)base;
   T.d_tile = P.tile_diag[H];
+  T.bar = smem_addr(&s_bar);
   double dre = 0.0, dim_ = 0.0;
   // passes of at most R slabs (R accumulators per thread stay in registers); all slabs but the very last are complete
   const int n_slab = (int)((size + THREADS - 1) / THREADS);
 #pragma unroll 1
   for (int s0 = 0; s0 < n_slab; s0 += R) {
     const int nfull = min(R, n_slab - s0) - 1;
-    U1Dispatch<VecT, THREADS, R, R - 1>::run(nfull, P, T, y, dot_partials != nullptr, dre, dim_, s0);
+    U1Dispatch<VecT, THREADS, R, R - 1, TMA>::run(nfull, P, T, y, dot_partials != nullptr, dre, dim_, s0);
   }
 
   if (dot_partials) {
@@ -918,7 +1007,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
   P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
   P.ms_q = plan->ms_q.p; P.ms_amp = plan->ms_amp.p;
-  plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
+  plan->smem_bytes = (size_t)(tile_cap + 2) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
                      (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4 + U1_MAX_MS * (4 + 4 + 8 + 8);
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
   plan->supported = true;
@@ -942,9 +1031,9 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side) {
 
 constexpr int U1_THREADS = 512;
 
-template <typename VecT, int R>
+template <typename VecT, int R, bool TMA = false>
 static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, void* out, double* partials) {
-  auto kern = k2_apply_u1<VecT, U1_THREADS, R>;
+  auto kern = k2_apply_u1<VecT, U1_THREADS, R, TMA>;
   static thread_local size_t configured = 0;
   if (plan->smem_bytes > 48 * 1024 && configured < plan->smem_bytes) {
     ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
@@ -1112,7 +1201,11 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   }
   // rows per thread and pass: 7 (40 registers, 3 CTAs/SM) measured 8.94 ms vs 9.11 ms for 13 (64 registers, 2 CTAs/SM)
   static const int r_f64 = getenv("EDCUDA_U1_R") ? atoi(getenv("EDCUDA_U1_R")) : 7;
-  if (dtype == ED_F64 && r_f64 == 7) launch_u1<double, 7>(plan, P, n_launch, out, partials);
+  // EDCUDA_U1_TMA=1: stage the x tile with one bulk async copy (TMA) instead of the load / st.shared loop
+  static const int use_tma = getenv("EDCUDA_U1_TMA") ? atoi(getenv("EDCUDA_U1_TMA")) : 0;
+  if (dtype == ED_F64 && r_f64 == 7 && use_tma) launch_u1<double, 7, true>(plan, P, n_launch, out, partials);
+  else if (dtype == ED_C128 && use_tma) launch_u1<c128, 7, true>(plan, P, n_launch, out, partials);
+  else if (dtype == ED_F64 && r_f64 == 7) launch_u1<double, 7>(plan, P, n_launch, out, partials);
   else if (dtype == ED_F64 && r_f64 == 5) launch_u1<double, 5>(plan, P, n_launch, out, partials);
   else if (dtype == ED_F64) launch_u1<double, 13>(plan, P, n_launch, out, partials);
   else launch_u1<c128, 7>(plan, P, n_launch, out, partials);

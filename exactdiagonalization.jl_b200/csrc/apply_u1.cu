@@ -61,7 +61,7 @@ struct U1Params {
   int n_ll; double ll_amp[U1_MAX_CLASSES];
   const uint32_t* ell[U1_MAX_CLASSES];     // class tables: two consecutive slots per 32-bit word
   const uint8_t* ell_cnt[U1_MAX_CLASSES];  // slot PAIRS used per 32-row group
-  const uint32_t* ell_ofs;                 // [n_ll * (k+1)] start of popcount p inside ell[c]
+  const uint32_t* ell_ofs;                 // [n_ll * (k+1)] start of popcount p inside ell[c] (multiple of 32 words)
   int n_hh;   const uint8_t* hh_p; const uint8_t* hh_q; const double* hh_amp;   // exchange bonds inside H
   int n_mx;   const uint8_t* mx_q; const double* mx_amp; const uint16_t* mx_tab; // straddling exchange bonds (gathered)
   // straddling bonds whose low site is bit k-1: the firing rows are a contiguous block of the tile and so are their
@@ -185,43 +185,12 @@ struct U1Tile {
   int p_low;
   int64_t base;
   double d_tile;
-  uint32_t bar;        // shared-memory address of the mbarrier the bulk copy of the x tile completes on (TMA staging)
 };
-
-// ---- TMA (bulk async copy) staging of the x tile ---------------------------------------------------------
-// One thread arms an mbarrier with the byte count and issues ONE cp.async.bulk global -> shared for the 16-byte
-// aligned middle of the tile; the copy runs on the TMA unit while the CTA builds its bond lists and consumes the
-// neighbour streams (which do not need the tile), and every thread waits on the barrier right before its first
-// shared-memory read.  No LSU instructions, no registers, no st.shared for the staging.
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // make the init visible to the async (TMA) proxy
-}
-__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
 
 // Slab body.  Slab r holds rows i = tid + r*THREADS.  NF = number of COMPLETE slabs of this tile (compile time:
 // constant offsets, no predicates, NF+1 independent loads in flight per thread and bond).  The last, partial slab is
 // addressed through the clamped per-thread index `it`, so every load stays in bounds; only its store is predicated.
-template <typename VecT, int THREADS, int NF, bool TMA>
+template <typename VecT, int THREADS, int NF>
 __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<VecT>& T,
                                              VecT* __restrict__ y, bool want_dot, double& dre, double& dim_, int slab0) {
   constexpr int CH = sizeof(VecT) == 8 ? 6 : 3;   // loads issued back to back before their FMAs (register budget)
@@ -323,8 +292,15 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
       vec_fma(acc_t, a, vt);
     }
   };
-  // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers
+  // exchange bonds inside the low k bits: ELL table of local columns (top bond first), shared-memory gathers.
+  //  * a table word holds the BYTE offsets (8 * column) of two slots, so a gather is mask/shift + LDS [offset + base];
+  //  * every slot row starts on a 128-byte boundary (row stride = size rounded up to 32 words): one line per warp load.
+  // Measured and dropped: stopping every slab at the slot count of its own 32-row group (16 % fewer slot pairs, but the
+  // per-slab predicates become branches: 8.14 ms vs 7.90 ms).
   auto part_low = [&]() {
+    constexpr int SH = sizeof(VecT) == 16 ? 1 : 0;
+    const char* xsb = reinterpret_cast<const char*>(xs);
+    const uint32_t size_pad = (size + 31u) & ~31u;
 #pragma unroll 1
     for (int c = 0; c < P.n_ll; ++c) {
       const uint8_t* cnt = P.ell_cnt[c] + T.gofs;
@@ -345,11 +321,14 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
             if (r0 + cc < NF) j[cc] = __ldg(et + (r0 + cc) * THREADS);
 #pragma unroll
           for (int cc = 0; cc < CH; ++cc)
-            if (r0 + cc < NF) { vec_fma(acc[r0 + cc], a, xs[j[cc] & 0xFFFFu]); vec_fma(acc[r0 + cc], a, xs[j[cc] >> 16]); }
+            if (r0 + cc < NF) {
+              vec_fma(acc[r0 + cc], a, *reinterpret_cast<const VecT*>(xsb + ((j[cc] & 0xFFFFu) << SH)));
+              vec_fma(acc[r0 + cc], a, *reinterpret_cast<const VecT*>(xsb + ((j[cc] >> 16) << SH)));
+            }
         }
-        vec_fma(acc_t, a, xs[jt & 0xFFFFu]);
-        vec_fma(acc_t, a, xs[jt >> 16]);
-        e += size;
+        vec_fma(acc_t, a, *reinterpret_cast<const VecT*>(xsb + ((jt & 0xFFFFu) << SH)));
+        vec_fma(acc_t, a, *reinterpret_cast<const VecT*>(xsb + ((jt >> 16) << SH)));
+        e += size_pad;
       }
     }
   };
@@ -383,22 +362,11 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
     }
   };
 
-  if (TMA) {
-    // everything that reads other tiles first (global loads in flight while the bulk copy of this tile lands),
-    // then wait for the tile and do the shared-memory parts
-    part_high();
-    part_block();
-    part_straddle();
-    mbar_wait(T.bar, 0);                     // completed once per CTA: later passes see the finished phase at once
-    part_diag();
-    part_low();
-  } else {
-    part_diag();
-    part_high();
-    part_block();
-    part_low();
-    part_straddle();
-  }
+  part_diag();
+  part_high();
+  part_block();
+  part_low();
+  part_straddle();
 
   // store (row-owner writes)
   const int64_t row0 = (int64_t)T.base + tid;
@@ -425,29 +393,26 @@ __device__ __forceinline__ void u1_tile_body(const U1Params& P, const U1Tile<Vec
   }
 }
 
-template <typename VecT, int THREADS, int R, int NF, bool TMA>
+template <typename VecT, int THREADS, int R, int NF>
 struct U1Dispatch {
   static __device__ __forceinline__ void run(int nfull, const U1Params& P, const U1Tile<VecT>& T, VecT* y,
                                              bool want_dot, double& dre, double& dim_, int slab0) {
-    if (nfull == NF) u1_tile_body<VecT, THREADS, NF, TMA>(P, T, y, want_dot, dre, dim_, slab0);
-    else U1Dispatch<VecT, THREADS, R, NF - 1, TMA>::run(nfull, P, T, y, want_dot, dre, dim_, slab0);
+    if (nfull == NF) u1_tile_body<VecT, THREADS, NF>(P, T, y, want_dot, dre, dim_, slab0);
+    else U1Dispatch<VecT, THREADS, R, NF - 1>::run(nfull, P, T, y, want_dot, dre, dim_, slab0);
   }
 };
-template <typename VecT, int THREADS, int R, bool TMA>
-struct U1Dispatch<VecT, THREADS, R, -1, TMA> {
+template <typename VecT, int THREADS, int R>
+struct U1Dispatch<VecT, THREADS, R, -1> {
   static __device__ __forceinline__ void run(int, const U1Params&, const U1Tile<VecT>&, VecT*, bool, double&, double&, int) {}
 };
 
 // One CTA = one tile of C(k, p_low) contiguous rows; R = ceil(tile_cap / THREADS) bounds the slabs per thread.
-// TMA = true: the x tile is staged by one bulk async copy (see tma_load_1d) instead of the load/st.shared loop.
-template <typename VecT, int THREADS, int R, bool TMA>
+template <typename VecT, int THREADS, int R>
 __global__ void __launch_bounds__(THREADS, (R <= 7 && sizeof(VecT) == 8) ? 3 : 2)
 k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // tile_cap + 2 elements: the tile, the zero the ELL padding points at, and one element of slack so that the tile can
-  // start at an odd element (TMA staging keeps the 16-byte phase of the global address)
-  VecT* xs = reinterpret_cast<VecT*>(smem_raw);
-  double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 2);
+  VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
+  double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 1);
   double* mx_amp = hh_amp + U1_MAX_HH;
   double* mq_coef = mx_amp + U1_MAX_MX;
   double* s_dval = mq_coef + U1_MAX_MQ;                                // 256
@@ -460,7 +425,6 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   double* ms_amp = reinterpret_cast<double*>(ms_len + U1_MAX_MS);
   const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + U1_MAX_MS);
   __shared__ int s_counts[4];
-  __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x;
   const uint32_t H = P.tile_H[P.tile_order ? P.tile_order[blockIdx.x] : P.tile_first + blockIdx.x];
@@ -469,22 +433,6 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
   const uint64_t base = P.tile_base[H];
   const int k = P.k;
-
-  // ---- x tile: bulk async copy issued before anything else (TMA staging) ------------------------------------
-  // The copy needs 16-byte aligned addresses and sizes: xs keeps the phase of the global address (xs = smem + head
-  // elements), the aligned middle goes through the TMA unit, an odd first / last element through plain loads.
-  const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
-  uint32_t tma_bytes = 0, tma_head = 0;
-  if (TMA) {
-    tma_head = (uint32_t)((reinterpret_cast<uintptr_t>(xo) & 15u) / sizeof(VecT));   // 0, or 1 for an odd double
-    if (sizeof(VecT) == 8) xs += tma_head;
-    if (size > tma_head) tma_bytes = (uint32_t)(((size - tma_head) * sizeof(VecT)) & ~(size_t)15);
-    if (tid == 96) {
-      mbar_init(smem_addr(&s_bar), 1);
-      if (tma_bytes) tma_load_1d(smem_addr(xs + tma_head), xo + tma_head, tma_bytes, smem_addr(&s_bar));
-      else mbar_arrive(smem_addr(&s_bar));              // nothing to copy: complete the phase so that waits fall through
-    }
-  }
 
   // ---- prologue: per-tile bond lists (deterministic ballot compaction), x tile --------------------------
   if (tid < 32) {
@@ -581,19 +529,12 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   if (P.stream_mode == 2) {                             // remote pass: most tiles have nothing to add
     __syncthreads();
     if (s_counts[0] + s_counts[2] + s_counts[3] == 0) {
-      if (TMA) mbar_wait(smem_addr(&s_bar), 0);               // never leave the CTA with a bulk copy in flight
       if (dot_partials && tid == 0) { dot_partials[2 * blockIdx.x] = 0.0; dot_partials[2 * blockIdx.x + 1] = 0.0; }
       return;
     }
   }
-  if (TMA) {
-    // elements the bulk copy does not cover (at most one at either end; the whole tile when it is tiny)
-    const uint32_t done_hi = tma_head + (uint32_t)(tma_bytes / sizeof(VecT));
-    if (tid >= 128) {
-      for (uint32_t i = tid - 128; i < size; i += THREADS - 128)
-        if (i < tma_head || i >= done_hi) xs[i] = ldg_val(xo + i);
-    }
-  } else {
+  {
+    const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
   }
   if (tid == 0) xs[size] = vzero((VecT*)nullptr);
@@ -608,14 +549,13 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   T.s_dval = s_dval;
   T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = (int64_t)base;
   T.d_tile = P.tile_diag[H];
-  T.bar = smem_addr(&s_bar);
   double dre = 0.0, dim_ = 0.0;
   // passes of at most R slabs (R accumulators per thread stay in registers); all slabs but the very last are complete
   const int n_slab = (int)((size + THREADS - 1) / THREADS);
 #pragma unroll 1
   for (int s0 = 0; s0 < n_slab; s0 += R) {
     const int nfull = min(R, n_slab - s0) - 1;
-    U1Dispatch<VecT, THREADS, R, R - 1, TMA>::run(nfull, P, T, y, dot_partials != nullptr, dre, dim_, s0);
+    U1Dispatch<VecT, THREADS, R, R - 1>::run(nfull, P, T, y, dot_partials != nullptr, dre, dim_, s0);
   }
 
   if (dot_partials) {
@@ -721,8 +661,8 @@ int choose_k(int n_bits, int vec_bytes) {
     int v = atoi(e);
     if (v >= 1 && v <= 16) k = std::min(v, n_bits);
   }
-  // x tile must leave room for two CTAs per SM: <= 104 KB
-  while (k > 1 && binom_u64(k, k / 2) * (uint64_t)vec_bytes > 104 * 1024) --k;
+  // x tile must leave room for two CTAs per SM: <= 104 KB; the ELL table stores 8 * column in 16 bits
+  while (k > 1 && (binom_u64(k, k / 2) * (uint64_t)vec_bytes > 104 * 1024 || binom_u64(k, k / 2) * 8 > 65535)) --k;
   return k;
 }
 
@@ -869,9 +809,28 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
     }
     if (ll) lls.push_back({c.d, (uint32_t)(ll & lowmask), c.v});
   }
-  // classes with the same amplitude share one ELL table
-  std::map<double, std::vector<LL>> by_amp;
-  for (auto& l : lls) by_amp[l.amp].push_back(l);
+  // classes with the same amplitude share one ELL table (at most 60 bonds per class keeps the u8 pair counts small)
+  std::vector<std::pair<double, std::vector<LL>>> by_amp;
+  {
+    std::map<double, std::vector<LL>> grouped;
+    for (auto& l : lls) grouped[l.amp].push_back(l);
+    for (auto& kv : grouped) {
+      std::vector<LL> cur;
+      int n_cur = 0;
+      for (auto& l : kv.second) {
+        uint32_t m = l.mask;
+        while (m) {
+          const int room = 60 - n_cur;
+          uint32_t take = 0;
+          for (int t = 0; t < room && m; ++t) { const uint32_t low = m & (0u - m); take |= low; m &= ~low; }
+          cur.push_back({l.d, take, l.amp});
+          n_cur += __builtin_popcount(take);
+          if (n_cur == 60) { by_amp.push_back({kv.first, cur}); cur.clear(); n_cur = 0; }
+        }
+      }
+      if (!cur.empty()) by_amp.push_back({kv.first, cur});
+    }
+  }
   if ((int)by_amp.size() > U1_MAX_CLASSES) return plan;
   if ((int)hh_p.size() > U1_MAX_HH || (int)mx_p.size() > U1_MAX_MX || (int)ms_q.size() > U1_MAX_MS) return plan;
   P.n_ms = (int)ms_q.size();
@@ -882,6 +841,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   std::vector<uint32_t> ell_ofs((size_t)std::max(P.n_ll, 1) * (k + 1), 0);
   plan->ell.resize(P.n_ll);
   plan->ell_cnt.resize(P.n_ll);
+  uint32_t max_pairs = 0;
   {
     int c = 0;
     std::vector<uint16_t> nb;
@@ -911,14 +871,19 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
           g = std::max<uint8_t>(g, (uint8_t)((lists[i].size() + 1) / 2));
         }
         const uint32_t maxpair = (maxslot + 1) / 2;
+        max_pairs = std::max(max_pairs, maxpair);
+        // every slot row starts on a 128-byte boundary: row stride = size rounded up to 32 words, class start likewise
+        const uint32_t size_pad = (size + 31u) & ~31u;
         ell_ofs[(size_t)c * (k + 1) + p] = (uint32_t)table.size();
         const size_t start = table.size();
-        table.resize(start + (size_t)maxpair * size, (uint32_t)size | ((uint32_t)size << 16));   // padding -> xs[size] == 0
+        // entries are byte offsets 8 * column (c128 tiles shift once more in the kernel); padding -> xs[size] == 0
+        table.resize(start + (size_t)maxpair * size_pad, (uint32_t)(8 * size) | ((uint32_t)(8 * size) << 16));
         for (uint32_t i = 0; i < size; ++i)
           for (size_t sl = 0; sl < lists[i].size(); ++sl) {
-            uint32_t& wd = table[start + (sl / 2) * size + i];
-            if (sl & 1) wd = (wd & 0x0000FFFFu) | ((uint32_t)lists[i][sl] << 16);
-            else wd = (wd & 0xFFFF0000u) | lists[i][sl];
+            uint32_t& wd = table[start + (sl / 2) * size_pad + i];
+            const uint32_t off = 8u * lists[i][sl];
+            if (sl & 1) wd = (wd & 0x0000FFFFu) | (off << 16);
+            else wd = (wd & 0xFFFF0000u) | off;
           }
       }
       if (table.empty()) table.push_back(0);
@@ -927,6 +892,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
       ++c;
     }
   }
+  if (max_pairs > 127) return plan;  // u8 slot-pair counts
   // straddling bonds: local column in the neighbouring tile, per (bond, value of the H bit)
   std::vector<uint16_t> mx_tab((size_t)std::max(P.n_mx, 1) * 2 * nlow, 0xFFFF);
   for (int e = 0; e < P.n_mx; ++e)
@@ -1007,7 +973,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
   P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
   P.ms_q = plan->ms_q.p; P.ms_amp = plan->ms_amp.p;
-  plan->smem_bytes = (size_t)(tile_cap + 2) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
+  plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
                      (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4 + U1_MAX_MS * (4 + 4 + 8 + 8);
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
   plan->supported = true;
@@ -1031,9 +997,9 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side) {
 
 constexpr int U1_THREADS = 512;
 
-template <typename VecT, int R, bool TMA = false>
+template <typename VecT, int R>
 static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, void* out, double* partials) {
-  auto kern = k2_apply_u1<VecT, U1_THREADS, R, TMA>;
+  auto kern = k2_apply_u1<VecT, U1_THREADS, R>;
   static thread_local size_t configured = 0;
   if (plan->smem_bytes > 48 * 1024 && configured < plan->smem_bytes) {
     ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
@@ -1200,14 +1166,8 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
     partials = plan->partials.p;
   }
   // rows per thread and pass: 7 (40 registers, 3 CTAs/SM) measured 8.94 ms vs 9.11 ms for 13 (64 registers, 2 CTAs/SM)
-  static const int r_f64 = getenv("EDCUDA_U1_R") ? atoi(getenv("EDCUDA_U1_R")) : 7;
-  // EDCUDA_U1_TMA=1: stage the x tile with one bulk async copy (TMA) instead of the load / st.shared loop
-  static const int use_tma = getenv("EDCUDA_U1_TMA") ? atoi(getenv("EDCUDA_U1_TMA")) : 0;
-  if (dtype == ED_F64 && r_f64 == 7 && use_tma) launch_u1<double, 7, true>(plan, P, n_launch, out, partials);
-  else if (dtype == ED_C128 && use_tma) launch_u1<c128, 7, true>(plan, P, n_launch, out, partials);
-  else if (dtype == ED_F64 && r_f64 == 7) launch_u1<double, 7>(plan, P, n_launch, out, partials);
-  else if (dtype == ED_F64 && r_f64 == 5) launch_u1<double, 5>(plan, P, n_launch, out, partials);
-  else if (dtype == ED_F64) launch_u1<double, 13>(plan, P, n_launch, out, partials);
+  // and 8.26 vs 10.39 ms for 5 (4 CTAs/SM); only R = 7 is instantiated
+  if (dtype == ED_F64) launch_u1<double, 7>(plan, P, n_launch, out, partials);
   else launch_u1<c128, 7>(plan, P, n_launch, out, partials);
   if (alpha_dot) ed_reduce_pairs(partials, n_launch, alpha_dot);
 }

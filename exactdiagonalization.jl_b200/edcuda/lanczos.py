@@ -343,12 +343,27 @@ class P2PShardedMatvec:
         return y_local
 
     def close(self):
+        """Collective: every rank stops using the shared buffers, then unmaps its peers' memory.  Call it before the
+        object goes away -- an owner that frees a buffer its peers still map, and later exports a new buffer that
+        reuses the allocation, makes the peers' next ed_ipc_open_handle fail with "resource already mapped"."""
         self.torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier(group=self.group)
+        self._unmap()
+        if self.world > 1:
+            self.dist.barrier(group=self.group)      # nobody frees its buffers before every peer has unmapped them
+
+    def _unmap(self):
         for p in self._opened:
             lib.ed_ipc_close_handle(C.c_void_p(p))
         self._opened = []
+
+    def __del__(self):
+        # last resort when close() was not called: at least drop this process's mappings of the peers' buffers
+        try:
+            self._unmap()
+        except Exception:
+            pass
 
 
 class ShardedLanczos:
@@ -372,6 +387,11 @@ class ShardedLanczos:
     def _ed_stream(self):
         torch = self.mv.torch
         check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
+
+    def close(self):
+        """Collective (see P2PShardedMatvec.close); a no-op for the all-gather exchange."""
+        if self.p2p:
+            self.mv.close()
 
     def run(self, n_steps: int, seed: int = 0, v0_local=None, n_ritz: int = 4) -> LanczosResult:
         mv, torch, dist = self.mv, self.mv.torch, self.mv.dist

@@ -944,6 +944,17 @@ def test_sharded_lanczos_world1_matches_library_driver(gpu_ed, golden):
 
 
 def _nccl_worker(rank, world, port, q):
+    """A failing rank reports its traceback through the queue instead of leaving its peers blocked in a collective."""
+    try:
+        _nccl_worker_body(rank, world, port, q)
+    except BaseException:                                  # noqa: BLE001 - forwarded to the parent, then the process dies
+        import os, traceback
+        q.put(("error", rank, traceback.format_exc()))
+        q.close(); q.join_thread()
+        os._exit(1)
+
+
+def _nccl_worker_body(rank, world, port, q):
     import os, sys
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -960,7 +971,9 @@ def _nccl_worker(rank, world, port, q):
     hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
     from edcuda.lanczos import P2PShardedMatvec
     res = ShardedLanczos(ed.represent(hsr, h), rank, world).run(120, seed=4)
-    res_p = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="p2p").run(120, seed=4)
+    sl_p = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="p2p")
+    res_p = sl_p.run(120, seed=4)
+    sl_p.close()          # collective: peers unmap the shared buffers before their owner frees them
     pm = P2PShardedMatvec(ed.represent(hsr, h), rank, world, n_buffers=1)
     xp = pm.x_buffer(0)
     for lo, hi, off in pm.local_ranges:
@@ -989,7 +1002,9 @@ def _nccl_worker(rank, world, port, q):
     assert float((yd - yp).abs().max()) <= 1e-12 * float(yp.abs().max())
     assert abs(float(dotd[0]) - float(dotp[0])) < 1e-9 * float(xp.norm() * yp.norm())
     pd.close()
-    res_d = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="dma").run(120, seed=4)
+    sl_d = ShardedLanczos(ed.represent(hsr, h), rank, world, exchange="dma")
+    res_d = sl_d.run(120, seed=4)
+    sl_d.close()
     assert abs(res_d.ritz[0] - res_p.ritz[0]) < 1e-10
     mv = ShardedMatvec(ed.represent(hsr, h), rank, world)
     x = torch.arange(mv.lo, mv.hi, dtype=torch.float64, device="cuda").sin()
@@ -999,7 +1014,7 @@ def _nccl_worker(rank, world, port, q):
     ys = [None] * world
     dist.all_gather_object(ys, y.cpu().numpy())
     if rank == 0:
-        q.put((res.alpha, res.beta, res.ritz, np.concatenate(ys), res_p.alpha, res_p.beta, res_p.ritz, np.concatenate(yps)))
+        q.put(("ok", res.alpha, res.beta, res.ritz, np.concatenate(ys), res_p.alpha, res_p.beta, res_p.ritz, np.concatenate(yps)))
     dist.destroy_process_group()
 
 
@@ -1020,7 +1035,15 @@ def test_multi_gpu_row_sharding_nccl(gpu_ed):
     procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    alpha, beta, ritz, y, alpha_p, beta_p, ritz_p, y_p = q.get(timeout=300)
+    try:
+        msg = q.get(timeout=240)
+    except Exception:
+        msg = ("error", -1, "no rank reported within 240 s")
+    if msg[0] != "ok":
+        for p in procs:
+            p.terminate()
+        pytest.fail(f"rank {msg[1]} failed:\n{msg[2]}")
+    _, alpha, beta, ritz, y, alpha_p, beta_p, ritz_p, y_p = msg
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0

@@ -708,7 +708,7 @@ def _c_oracle_apply(n, n_dn, op, x, side=0):
 
 
 @pytest.mark.parametrize("n,n_dn,model", [(20, 10, "xxz"), (20, 7, "j1j2_field"), (16, 8, "square"), (16, 5, "triangular"),
-                                          (24, 12, "xxz"), (13, 6, "open_chain_disorderfree")])
+                                          (24, 12, "xxz"), (13, 6, "open_chain_disorderfree"), (24, 12, "long_range")])
 def test_fast_path_vs_c_oracle(gpu_ed, n, n_dn, model):
     """The tiled U(1) kernel against the oracle's C twin (reference algorithm) at sizes the Python oracle cannot
     reach, for every bond geometry the lowering distinguishes (several distance classes, wrap bonds, fields)."""
@@ -724,6 +724,10 @@ def test_fast_path_vs_c_oracle(gpu_ed, n, n_dn, model):
         h = ed.models.heisenberg_bonds(hs, L.square_bonds(4, 4))
     elif model == "triangular":
         h = ed.models.heisenberg_bonds(hs, L.triangular_bonds(4, 4), 0.25)
+    elif model == "long_range":
+        # one amplitude, 63 bonds inside the low 14 bits: the ELL class is split at 60 bonds
+        h = ed.simplify(sum((ed.models.heisenberg_bonds(hs, L.chain_bonds(n, dist)) for dist in range(2, 7)),
+                            ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 1))))
     else:
         h = ed.models.xxz_bonds(hs, L.chain_bonds(n, 1, periodic=False), 0.8, -1.1)
     hsr = ed.represent(ed.HilbertSpaceSector(hs, n - 2 * n_dn))
@@ -734,6 +738,12 @@ def test_fast_path_vs_c_oracle(gpu_ed, n, n_dn, model):
     basis, exp = _c_oracle_apply(n, n_dn, h, x)
     assert np.array_equal(hsr.download(0, d), basis)
     fast, gen = ed.represent(hsr, h), ed.represent(hsr, h).set_kernel(1)
+    if model == "long_range":     # the tiled kernel really takes this operator: only its plan hands out wrap-aware ranges
+        import ctypes as C
+        from edcuda._lib import lib, check
+        lo2, hi2, nr = (C.c_int64 * 2)(), (C.c_int64 * 2)(), C.c_int32()
+        check(lib.ed_oprep_suggest_row_ranges(fast._handle, ed.ED_F64, 2, 0, lo2, hi2, C.byref(nr)))
+        assert nr.value == 2
     y_fast, y_gen = np.zeros(d), np.zeros(d)
     ed.mul_b(y_fast, fast, x)
     ed.mul_b(y_gen, gen, x)
@@ -799,7 +809,8 @@ def test_fast_path_segmented_input_single_gpu(gpu_ed, n, n_dn, model):
     assert rel_err(np.concatenate(outs), exp) < TOL
     assert abs(sum(dots) - float(np.dot(x, exp))) < 1e-10 * np.linalg.norm(x) * np.linalg.norm(exp)
 
-@pytest.mark.parametrize("n,n_dn,model,world", [(20, 10, "xxz", 2), (22, 11, "xxz", 4), (20, 7, "j1j2", 3), (18, 9, "open", 2)])
+@pytest.mark.parametrize("n,n_dn,model,world", [(20, 10, "xxz", 2), (22, 11, "xxz", 4), (20, 7, "j1j2", 3), (18, 9, "open", 2),
+                                                (24, 12, "xxz", 8)])     # 8 ranks x 2 ranges = the 16-segment limit
 def test_wrap_aware_row_ranges_single_gpu(gpu_ed, n, n_dn, model, world):
     """ed_oprep_suggest_row_ranges on one device: for a ring every "rank" gets two tile-aligned ranges (same high bits in
     both halves of the basis) that tile the basis exactly and keep the wrapping bond local; an open chain gets the plain

@@ -269,9 +269,15 @@ struct CsrCache {
   int side = 0;
   int64_t row_lo = 0, row_hi = 0, nnz = 0;
   bool val_complex = false;
-  DevBuf<int64_t> rowptr;   // 0-based, row_hi-row_lo+1 entries
+  DevBuf<int64_t> rowptr;   // 0-based, row_hi-row_lo+1 entries (released when the matrix is column-blocked)
   DevBuf<int32_t> col;      // 0-based
   DevBuf<double> val;       // nnz doubles or nnz (re,im) pairs
+  // column blocking (x larger than the L2): the entries regrouped block-major -- block b holds, row by row, the entries
+  // whose column lies in [b * block_cols, (b + 1) * block_cols) -- so that one pass per block gathers x from an L2-sized window
+  int n_blocks = 1;
+  int64_t block_cols = 0;
+  DevBuf<uint32_t> blk_rowptr;        // [n_blocks][n_rows + 1], relative to blk_base[b]
+  std::vector<int64_t> blk_base;      // [n_blocks + 1] first entry of block b in col / val
 };
 
 struct ed_oprep {

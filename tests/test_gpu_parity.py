@@ -1120,9 +1120,14 @@ def test_triangular_6x6_full_size(gpu_ed, golden):
 
 
 # ------------------------------------------------------------------ cached CSR (SpMV) path
-def test_cached_matrix_apply_matches_matrix_free(gpu_ed):
+@pytest.mark.parametrize("block_cols", [None, 37])
+def test_cached_matrix_apply_matches_matrix_free(gpu_ed, monkeypatch, block_cols):
+    """block_cols = 37 forces the column-blocked form of the cached matrix (one SpMV pass per L2-sized window of x; at
+    full size it only switches on when x outgrows the L2) on these small matrices: 25 and 3 blocks."""
     ed = gpu_ed
     from edcuda.lanczos import lanczos
+    if block_cols:
+        monkeypatch.setenv("EDCUDA_CSR_BLOCK_COLS", str(block_cols))
     n = 12
     hs, h = ed.models.j1j2_chain(n, 0.5)
     hs_o, a = oracle_spin_chain(n)

@@ -12,7 +12,10 @@ WANT = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum',
  'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio','smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
  'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio','smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
  'smsp__thread_inst_executed_per_inst_executed.ratio','l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum','l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
- 'smsp__warps_eligible.avg.per_cycle_active','sm__maximum_warps_per_active_cycle_pct']
+ 'smsp__warps_eligible.avg.per_cycle_active','sm__maximum_warps_per_active_cycle_pct',
+ 'lts__t_sectors.sum','lts__t_bytes.sum','lts__t_sectors_op_read.sum','lts__t_sectors_op_write.sum','l1tex__data_pipe_lsu_wavefronts.sum',
+ 'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum','l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum','smsp__inst_executed_pipe_lsu.sum',
+ 'lts__t_sectors_srcunit_tex.sum','lts__t_sectors_srcunit_tex_lookup_hit.sum','lts__t_sectors_srcunit_tex_lookup_miss.sum']
 def main(rep):
     out = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
     rows = list(csv.reader(out.splitlines()))

@@ -13,7 +13,9 @@ g = torch.Generator(device="cuda").manual_seed(1)
 x = torch.randn(d, dtype=torch.complex128, device="cuda", generator=g) / math.sqrt(d)
 y = torch.empty_like(x)
 ref = None
-for cols in sys.argv[1:] or ["0", "7100000", "5300000", "3540000"]:
+args = [a for a in sys.argv[1:] if not a.startswith("--lanes=")]
+lanes_arg = [tuple(int(v) for v in a.split("=")[1].split(",")) for a in sys.argv[1:] if a.startswith("--lanes=")]
+for cols in args or ["0", "7100000", "5300000", "3540000"]:
     os.environ.pop("EDCUDA_CSR_NOBLOCK", None)
     os.environ.pop("EDCUDA_CSR_BLOCK_COLS", None)
     if cols == "0":
@@ -25,7 +27,7 @@ for cols in sys.argv[1:] or ["0", "7100000", "5300000", "3540000"]:
     ropr.cache_matrix()
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t0
-    for lanes in ((8,) if cols == "0" else (1, 2, 4, 8)):
+    for lanes in ((8,) if cols == "0" else (lanes_arg[0] if lanes_arg else (1, 2, 4, 8))):
         os.environ["EDCUDA_CSR_LANES"] = str(lanes)
         for _ in range(3):
             ed.mul_b(y, ropr, x)

@@ -121,12 +121,16 @@ k6b_canonicalize(int n_ops, const uint64_t* __restrict__ lut6, const int32_t* __
 // the n1 x n2 translations as ALU steps on the image (Tx = rotate every n1-bit field by one, Ty = rotate the word by
 // n1).  |G| / (n1 n2) LUT images per word instead of |G|: the sweep moves from the shared-memory pipe (bank
 // conflicts of the LUT gathers) to the integer pipes.  tinv[(j*n2 + b)*n1 + a] = inverse index of Tx^a Ty^b p_j.
-template <int NCH>
+// N1 x N2 > 0: lattice shape known at compile time (6x6, 4x4): both translation loops are fully unrolled, the masks are
+// immediates and the rotation that would only restore the starting image (last Tx of a row sweep, last Ty) is skipped.
+template <int NCH, int N1, int N2>
 __global__ void __launch_bounds__(256)
-k6b_canonicalize_tr(int n_cos, int n1, int n2, int n_bits, const uint64_t* __restrict__ lut6c, const int32_t* __restrict__ tinv,
+k6b_canonicalize_tr(int n_cos, int n1_rt, int n2_rt, int n_bits_rt, const uint64_t* __restrict__ lut6c, const int32_t* __restrict__ tinv,
                     int64_t n_words, uint64_t* __restrict__ words, uint16_t* __restrict__ garg) {
   constexpr int W = 4;          // words per thread
   constexpr int CB = 4;         // cosets staged per barrier
+  constexpr bool FIXED = N1 > 0;
+  const int n1 = FIXED ? N1 : n1_rt, n2 = FIXED ? N2 : n2_rt, n_bits = FIXED ? N1 * N2 : n_bits_rt;
   extern __shared__ __align__(16) unsigned char k6_smem[];
   uint64_t* s_lut = reinterpret_cast<uint64_t*>(k6_smem);                   // [2][CB * NCH * 64]
   int32_t* s_inv = reinterpret_cast<int32_t*>(s_lut + 2 * CB * NCH * 64);   // [2][CB * n1 * n2]
@@ -135,7 +139,9 @@ k6b_canonicalize_tr(int n_cos, int n1, int n2, int n_bits, const uint64_t* __res
   const int64_t base = (int64_t)blockIdx.x * (256 * W);
   const uint64_t full = n_bits >= 64 ? ~0ull : ((1ull << n_bits) - 1ull);
   uint64_t m_lo = 0;
-  for (int y = 0; y < n2; ++y) m_lo |= 1ull << (n1 * y);
+#pragma unroll
+  for (int y = 0; y < (FIXED ? N2 : 64); ++y)
+    if (y < n2) m_lo |= 1ull << (n1 * y);
   const uint64_t m_hi = full & ~m_lo;
   uint64_t w[W], best[W];
   int besti[W];
@@ -176,12 +182,12 @@ k6b_canonicalize_tr(int n_cos, int n1, int n2, int n_bits, const uint64_t* __res
         for (int c = 0; c < NCH; ++c) v |= L[off[k][c]];
         im[k] = v;
       }
-#pragma unroll 1
+#pragma unroll(FIXED ? N2 : 1)
       for (int b = 0; b < n2; ++b) {
         uint64_t u[W];
 #pragma unroll
         for (int k = 0; k < W; ++k) u[k] = im[k];
-#pragma unroll 1
+#pragma unroll(FIXED ? N1 : 1)
         for (int a = 0; a < n1; ++a) {
           bool hit = false;
 #pragma unroll
@@ -194,11 +200,15 @@ k6b_canonicalize_tr(int n_cos, int n1, int n2, int n_bits, const uint64_t* __res
               else if (u[k] == best[k] && inv > besti[k]) besti[k] = inv;
             }
           }
+          if (!FIXED || a + 1 < N1) {
 #pragma unroll
-          for (int k = 0; k < W; ++k) u[k] = ((u[k] << 1) & m_hi) | ((u[k] >> (n1 - 1)) & m_lo);          // Tx
+            for (int k = 0; k < W; ++k) u[k] = ((u[k] << 1) & m_hi) | ((u[k] >> (n1 - 1)) & m_lo);        // Tx
+          }
         }
+        if (!FIXED || b + 1 < N2) {
 #pragma unroll
-        for (int k = 0; k < W; ++k) im[k] = ((im[k] << n1) | (im[k] >> (n_bits - n1))) & full;   // Ty
+          for (int k = 0; k < W; ++k) im[k] = ((im[k] << n1) | (im[k] >> (n_bits - n1))) & full;   // Ty
+        }
       }
     }
     __syncthreads();
@@ -359,9 +369,16 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
     if (sd.tr_on && nch <= 8) {
       const size_t smem = (size_t)2 * 4 * nch * 64 * 8 + (size_t)2 * 4 * sd.tr_n1 * sd.tr_n2 * 4;
       const int nb_ = parent->space.bits;
-      if (nch <= 4) ED_LAUNCH(k6b_canonicalize_tr<4>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
-      else if (nch <= 6) ED_LAUNCH(k6b_canonicalize_tr<6>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
-      else ED_LAUNCH(k6b_canonicalize_tr<8>, grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);
+#define ED_K6TR(NCH_, N1_, N2_)                                                                                               \
+      ED_LAUNCH((k6b_canonicalize_tr<NCH_, N1_, N2_>), grid_b, 256, smem, sd.tr_ncos, sd.tr_n1, sd.tr_n2, nb_, sd.tr_lut6.p, \
+                sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p)
+      const bool unrolled = !getenv("EDCUDA_K6_NOUNROLL") && nb_ == sd.tr_n1 * sd.tr_n2;
+      if (unrolled && sd.tr_n1 == 6 && sd.tr_n2 == 6 && nch == 6) ED_K6TR(6, 6, 6);
+      else if (unrolled && sd.tr_n1 == 4 && sd.tr_n2 == 4 && nch <= 4) ED_K6TR(4, 4, 4);
+      else if (nch <= 4) ED_K6TR(4, 0, 0);
+      else if (nch <= 6) ED_K6TR(6, 0, 0);
+      else ED_K6TR(8, 0, 0);
+#undef ED_K6TR
     }
     else if (nch <= 4) ED_LAUNCH(k6b_canonicalize<4>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
     else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);

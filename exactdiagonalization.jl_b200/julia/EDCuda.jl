@@ -345,4 +345,18 @@ function lanczos(opr::GpuOperatorRepresentation{S}, nsteps::Integer; seed::Integ
     return (alpha=alpha[1:done[]], beta=beta[1:done[]], ritz=ritz)
 end
 
+# ---------------------------------------------------------------------------------------------------------------
+# Cached matrix (not in the reference): keep the assembled rows on device so that repeated `mul!`s (Arpack, KrylovKit)
+# run as an SpMV instead of redoing the term walk / orbit searches; `side` = SIDE_LEFT for opr*x, SIDE_RIGHT for x*opr.
+function cache_matrix!(opr, side::Cint=SIDE_LEFT)
+    nnz = Ref{Int64}(0)
+    check(ccall((:ed_oprep_cache_matrix, libedcuda), Cint, (Ptr{Cvoid}, Int32, Ref{Int64}), opr.ptr, side, nnz))
+    return nnz[]
+end
+drop_cache!(opr) = (check(ccall((:ed_oprep_drop_cache, libedcuda), Cint, (Ptr{Cvoid},), opr.ptr)); opr)
+
+# Row shard of a representation (one process per GPU): apply!/mul! then read the full x and write rows lo+1:hi of out.
+set_rows!(opr, lo::Integer, hi::Integer) =
+    (check(ccall((:ed_oprep_set_rows, libedcuda), Cint, (Ptr{Cvoid}, Int64, Int64), opr.ptr, lo, hi)); opr)
+
 end # module

@@ -33,6 +33,27 @@ WORKLOADS = {
 }
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at N > 1), so the real
+    stdout is kept aside for emit() and file descriptor 1 is pointed at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def nnz_eff(n_sites: int, n_bonds: int) -> int:
     """D + n_bonds * 2 * C(N-2, N/2-1)."""
     return math.comb(n_sites, n_sites // 2) + n_bonds * 2 * math.comb(n_sites - 2, n_sites // 2 - 1)
@@ -171,7 +192,7 @@ def run_reference(args, w, name):
             "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": math.comb(n, n // 2)},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_reduced(args, w, name, ed, torch, np, rank, world, dev):
@@ -233,7 +254,7 @@ def run_reduced(args, w, name, ed, torch, np, rank, world, dev):
         return
     peak, src = peaks()
     alg = 40.0 * n_local                      # 8 B word + 16 B x + 16 B y per owned row
-    print(json.dumps({"metric": "H*v matvecs/sec", "value": 1e3 / ms, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
+    emit({"metric": "H*v matvecs/sec", "value": 1e3 / ms, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                       "dtype": "c128", "data": "synthetic", "gnnz_per_s": nnz_total / (ms * 1e-3) / 1e9,
                       "config": {"workload": name, "description": w["desc"], "dim": d, "parent_dim": hsr.dimension,
@@ -249,7 +270,7 @@ def run_reduced(args, w, name, ed, torch, np, rank, world, dev):
                       "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                    "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src, "kernel_ms": kms,
                                    "algorithmic_bytes_per_launch": alg},
-                      "gpu_launches": launches}))
+                      "gpu_launches": launches})
 
 
 def main():
@@ -267,6 +288,7 @@ def main():
     ap.add_argument("--lanczos", type=int, default=0,
                     help="also run this many device-resident Lanczos steps (sharded over the ranks) and report ms/step and the lowest Ritz value")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     name = args.workload
     w = WORKLOADS[name]
@@ -275,7 +297,7 @@ def main():
             # the reference keeps 32 B per PARENT state (9.08e9 states -> 290 GB of maps): not runnable on this host,
             # and the oracle's C twin only restates the plain-basis apply_parallel!
             if int(os.environ.get("RANK", "0")) == 0:
-                print(json.dumps({"impl": "reference", "unavailable": "reference algorithm needs ~360 GB of host memory for the 6x6 triangular parent space (SURVEY 8d); no CPU arm for this workload"}))
+                emit({"impl": "reference", "unavailable": "reference algorithm needs ~360 GB of host memory for the 6x6 triangular parent space (SURVEY 8d); no CPU arm for this workload"})
             return
         run_reference(args, w, name)
         return
@@ -482,7 +504,7 @@ def main():
             line["lanczos"] = lanczos_info
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w)
-        print(json.dumps(line))
+        emit(line)
     if p2p:
         mv.close()
     if world > 1:

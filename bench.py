@@ -1,13 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- H*v matvec throughput of the engine on the BASELINE.json headline workload.
+"""bench.py -- H*v matvec throughput of the engine on the BASELINE.json headline workloads.
 
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 
-Workload (N=1 default): XXZ chain L=32, Sz=0 sector (601,080,390 states, 192 terms) -- the configuration
-BASELINE.json's metric is quoted on; one "step" = one matrix-free matvec y = H x over the whole basis.
-N>1: the same problem row-sharded over N ranks (strong scaling): every step all-gathers x over NCCL and applies
-the local rows.  Prints ONE JSON line (rank 0).  `--impl reference` times the reference algorithm's CPU
-restatement (oracle/ed_oracle_c.c, OpenMP, all host threads) on a bounded row sample of the same workload.
+Headline workload: XXZ chain L=32, Sz=0 sector (601,080,390 states, 192 terms) -- the configuration BASELINE.json's metric
+is quoted on; one "step" = one matrix-free matvec y = H x over the whole basis.  N>1 (one process per GPU under torchrun):
+the same problem row-sharded over N ranks (strong scaling) through the library's multi-GPU context -- partition, halo
+copies over NVLink, NCCL fences and the Lanczos all-reduces all run inside libedcuda.so (torch.distributed only hands out
+the NCCL unique id).  The line also carries, as sub-objects, BASELINE's other named workloads at the same N: `lanczos`
+(config 5: 100 device-resident Lanczos steps), `tri6x6` (config 4: 6x6 triangular, k=0 A1, reduced matvec matrix-free
+and through the cached CSR) and, at N=1, `sparse` (configs 1-2 assembly times) and `parity_sample` (max relative error
+of the timed kernel's output against the oracle's C twin on sampled rows of the same x).
+`--impl reference` times the reference algorithm's CPU restatement (oracle/ed_oracle_c.c, OpenMP, every host core) on a
+bounded row sample of the same workload; it never loads libedcuda.so.  Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -19,10 +24,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
 
 WORKLOADS = {
-    # name: (n_sites, builder, description)
     "xxz_chain_L32_sz0": dict(n=32, kind="xxz", desc="XXZ chain L=32 (Delta=1), Sz=0, periodic, Pauli normalisation"),
     "j1j2_chain_L28_sz0": dict(n=28, kind="j1j2", desc="J1-J2 chain L=28 (J2=0.5), Sz=0"),
     "xxz_chain_L24_sz0": dict(n=24, kind="xxz", desc="XXZ chain L=24, Sz=0 (small, for quick checks)"),
@@ -31,7 +34,6 @@ WORKLOADS = {
     "xxz_chain_L16_sz0": dict(n=16, kind="xxz", desc="Heisenberg chain L=16, Sz=0 (reference CPU-runnable case)"),
     "tri6x6_k0A1_sz0": dict(n=36, kind="tri", desc="6x6 triangular Heisenberg, T x| C6v k=0 A1, Sz=0: reduced matvec (ComplexF64), |G|=432"),
 }
-
 
 _JSON_FD = None
 
@@ -54,9 +56,29 @@ def emit(obj):
         os.write(_JSON_FD, data)
 
 
+def host_cores() -> int:
+    """cores this process may run on -- NOT OMP_NUM_THREADS, which torchrun sets to 1 for its workers"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def nnz_eff(n_sites: int, n_bonds: int) -> int:
     """D + n_bonds * 2 * C(N-2, N/2-1)."""
     return math.comb(n_sites, n_sites // 2) + n_bonds * 2 * math.comb(n_sites - 2, n_sites // 2 - 1)
+
+
+def n_bonds_of(w) -> int:
+    return w["n"] if w["kind"] == "xxz" else 2 * w["n"]
+
+
+def base_config(name, w):
+    """identical in both arms (the driver compares the dicts): the workload, nothing about how it was run"""
+    n = w["n"]
+    if w["kind"] == "tri":
+        return {"workload": name, "description": w["desc"], "n_sites": n, "dim": 21029820, "n_terms": 648}
+    return {"workload": name, "description": w["desc"], "n_sites": n, "dim": math.comb(n, n // 2), "n_terms": 6 * n_bonds_of(w)}
 
 
 def peaks():
@@ -111,166 +133,197 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_model(ed, w):
+# ------------------------------------------------------------------------------------------ CPU arm (oracle only)
+def oracle_terms(w):
+    """the workload's term list from the ORACLE's operator algebra (simplify order): the CPU arm never imports the product"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ed_oracle as O
     n = w["n"]
-    if w["kind"] == "xxz":
-        hs, h = ed.models.xxz_chain(n, 1.0)
-        n_bonds = n
-    else:
-        hs, h = ed.models.j1j2_chain(n, 0.5)
-        n_bonds = 2 * n
-    return hs, h, n_bonds
+    hs, pauli = O.spin_half_system(n)
+
+    def bonds_op(bonds, j):
+        h = None
+        for (a, b) in bonds:
+            t = (2.0 * j) * (pauli(a, "+") * pauli(b, "-")) + (2.0 * j) * (pauli(a, "-") * pauli(b, "+")) + float(j) * (pauli(a, "z") * pauli(b, "z"))
+            h = t if h is None else h + t
+        return h
+
+    h = bonds_op([(i, (i + 1) % n) for i in range(n)], 1.0)
+    if w["kind"] == "j1j2":
+        h = h + bonds_op([(i, (i + 2) % n) for i in range(n)], 0.5)
+    return O.term_arrays(O.simplify(h))
 
 
 class CpuReference:
     """Reference-algorithm restatement (oracle C twin: term walk in order + binary search per hit + static row
-    partition = the reference's apply_parallel!) on a bounded contiguous row sample, all host threads."""
+    partition = the reference's apply_parallel!) on a bounded contiguous row sample, every core of the host."""
 
-    def __init__(self, w, threads=None):
+    def __init__(self, w, x=None):
+        os.environ["ED_ORACLE_NATIVE"] = "1"      # rebuilt on this machine with -march=native (falls back to the portable .so)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import numpy as np
         import ed_oracle_c as OC
-        sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
-        import edcuda as ed   # only for the model's term list (host code); no engine compute on this path
         self.np, self.OC = np, OC
-        if threads:
-            OC.set_num_threads(threads)
+        self.threads = host_cores()
+        OC.set_num_threads(self.threads)          # explicit: torchrun exports OMP_NUM_THREADS=1
         self.n = w["n"]
-        _, h, self.n_bonds = build_model(ed, w)
-        self.terms = h.arrays()
+        self.n_bonds = n_bonds_of(w)
+        self.terms = oracle_terms(w)
         self.basis = OC.basis_fixed_popcount(self.n, self.n // 2)
         self.dim = len(self.basis)
-        self.x = np.random.default_rng(20260717 + 5).standard_normal(self.dim)
-        # calibrate on a small slice in the middle of the basis
-        self.n0 = min(self.dim, 20000 * OC.num_threads())
-        self.rate = self.n0 / self._time(self.n0)          # rows per second
+        self.x = x if x is not None else np.random.default_rng(20260717 + 5).standard_normal(self.dim)
+        self.n0 = min(self.dim, 20000 * self.threads)
+        self.rate = self.n0 / self._time(self.n0)[0]          # rows per second (calibration slice)
 
-    def _time(self, rows):
-        lo = max(0, self.dim // 2 - rows // 2)
+    def _time(self, rows, lo=None):
+        lo = max(0, self.dim // 2 - rows // 2) if lo is None else lo
         out = self.np.zeros(rows)
         t0 = time.perf_counter()
         self.OC.apply(self.basis, self.terms, self.x, out, lo, lo + rows)
-        self._last = (lo, rows)
-        return time.perf_counter() - t0
+        return time.perf_counter() - t0, lo, out
 
     def sample(self, target_seconds):
-        OC = self.OC
         rows = int(min(self.dim, max(self.n0, self.rate * target_seconds)))
-        dt = self._time(rows)
-        lo, rows = self._last
+        dt, lo, _ = self._time(rows)
         matvec_s = dt * self.dim / rows
-        return {"value": 1.0 / matvec_s, "unit": "matvec/s", "cores": OC.num_threads(), "kind": "port",
-                "sample": f"rows [{lo},{lo + rows}) of {self.dim} ({rows / self.dim:.4%}) timed {dt:.2f}s on {OC.num_threads()} OpenMP threads, "
-                          f"extrapolated to the full matvec; reference-algorithm restatement (oracle/ed_oracle_c.c), not Julia",
+        return {"value": 1.0 / matvec_s, "unit": "matvec/s", "cores": self.threads, "kind": "port",
+                "sample": f"rows [{lo},{lo + rows}) of {self.dim} ({rows / self.dim:.4%}) timed {dt:.2f}s on {self.threads} OpenMP threads "
+                          f"(all cores of the host; OMP_NUM_THREADS ignored), extrapolated to the full matvec; reference-algorithm "
+                          f"restatement oracle/ed_oracle_c.c [{self.OC.BUILD}], not Julia (not installed)",
                 "seconds_per_matvec_extrapolated": matvec_s, "gnnz_per_s": nnz_eff(self.n, self.n_bonds) / matvec_s / 1e9}
 
-
-def cpu_baseline(w, target_seconds=12.0, threads=None):
-    return CpuReference(w, threads).sample(target_seconds)
+    def parity(self, y_rows, blocks):
+        """max |y - oracle| / max |oracle| over the given (lo, hi) row blocks; y_rows(lo, hi) -> numpy"""
+        worst, scale, total = 0.0, 0.0, 0
+        for lo, hi in blocks:
+            _, _, exp = self._time(hi - lo, lo)
+            worst = max(worst, float(self.np.max(self.np.abs(y_rows(lo, hi) - exp))))
+            scale = max(scale, float(self.np.max(self.np.abs(exp))))
+            total += hi - lo
+        return {"max_rel_err": worst / scale if scale > 0 else None, "rows": total, "blocks": len(blocks),
+                "against": "oracle/ed_oracle_c.c apply_parallel! restatement on the same x"}
 
 
 def run_reference(args, w, name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if w["kind"] == "tri":
+        # the reference keeps 32 B per PARENT state (9.08e9 states -> 290 GB of maps): not runnable on this host
+        emit({"impl": "reference", "unavailable": "reference algorithm needs ~360 GB of host memory for the 6x6 triangular parent space (SURVEY 8d); no CPU arm for this workload"})
+        return
     per_step = max(1.0, min(12.0, 150.0 / max(1, args.steps + args.warmup)))
     ref = CpuReference(w)
-    vals = []
-    cb = None
+    vals, cb = [], None
     for i in range(args.warmup + args.steps):
         cb = ref.sample(per_step)
         if i >= args.warmup:
             vals.append(cb["value"])
     v = sum(vals) / len(vals)
-    n = w["n"]
-    n_bonds = n if w["kind"] == "xxz" else 2 * n
     cb["value"] = v
-    line = {"impl": "reference", "metric": "H*v matvecs/sec", "value": v, "unit": "matvec/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "gnnz_per_s": nnz_eff(n, n_bonds) * v / 1e9,
-            "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": math.comb(n, n // 2)},
-            "cpu_baseline": cb,
-            "e2e": {"value": v, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    emit(line)
+    emit({"impl": "reference", "metric": "H*v matvecs/sec", "value": v, "unit": "matvec/s", "n_gpus": args.gpus,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+          "gnnz_per_s": nnz_eff(w["n"], n_bonds_of(w)) * v / 1e9, "config": base_config(name, w), "cpu_baseline": cb,
+          "e2e": {"value": v, "unit": "matvec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
-def run_reduced(args, w, name, ed, torch, np, rank, world, dev):
-    """Second headline workload (BASELINE config 4): matvec in the symmetry-reduced 6x6 triangular sector, rows
-    sharded over the ranks (strong scaling).  Every rank enumerates the reduced basis itself (no parent
-    materialisation), owns a contiguous row range, all-gathers x (336 MB) per matvec and applies its rows:
-    matrix-free (K6), then with the owned rows cached as CSR (ed_oprep_cache_matrix)."""
-    from edcuda.lanczos import ShardedMatvec
-    dist = torch.distributed if world > 1 else None
+# ------------------------------------------------------------------------------------------ engine arm
+def build_model(ed, w):
+    n = w["n"]
+    if w["kind"] == "xxz":
+        hs, h = ed.models.xxz_chain(n, 1.0)
+    else:
+        hs, h = ed.models.j1j2_chain(n, 0.5)
+    return hs, h
+
+
+def time_sharded(ctx, fn, warmup, steps):
+    """fn() enqueues one step on the context's streams; returns ms per step (device time, max over ranks)"""
+    for _ in range(warmup):
+        fn()
+    ctx.barrier()
+    ctx.timer_record(0)
+    for _ in range(steps):
+        fn()
+    ctx.timer_record(1)
+    return ctx.timer_elapsed(0, 1) / steps
+
+
+def bench_tri6x6(ed, np, ctx, steps, peak):
+    """BASELINE config 4: reduced matvec of the 6x6 triangular k=0 A1 sector, rows sharded over the ranks of ctx
+    (every rank enumerates the reduced basis itself; x all-gathered over NCCL per matvec): matrix-free (K6), then with
+    the owned rows cached as CSR."""
+    from edcuda.distributed import ShardedOperator
     t0 = time.perf_counter()
     hs, h = ed.models.heisenberg_triangular(6)
-    hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
-    rhsr = ed.symmetry_reduce(hsr, ed.lattices.triangular_space_group_irrep(6, "A1"))
-    t_reduce = time.perf_counter() - t0
-    d = rhsr.dimension
-    ropr = ed.represent(rhsr, h)
-    mv = ShardedMatvec(ropr, rank, world, np.complex128)
-    n_local = mv.hi - mv.lo
-    g = torch.Generator(device="cuda").manual_seed(20260717 + 4 + 1000 * rank)
-    x = torch.randn(n_local, dtype=torch.complex128, device=dev, generator=g) / math.sqrt(d)
-    y = torch.empty_like(x)
+    symops = ed.lattices.triangular_space_group_irrep(6, "A1")
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def make():
+        return ed.represent(ed.symmetry_reduce(ed.represent(ed.HilbertSpaceSector(hs, 0)), symops), h)
 
-    def timed(n_warm, n_steps):
-        for _ in range(n_warm):
-            mv.matvec(y, x)
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
-        l0 = ed.kernel_launch_count()
-        ev0.record()
-        for i in range(n_steps):
-            xf = mv.gather(x) if world > 1 else x
-            kev[i][0].record()
-            mv.apply_local(y, xf)
-            kev[i][1].record()
-        ev1.record()
-        barrier()
-        t = torch.tensor([ev0.elapsed_time(ev1) / n_steps, sum(a.elapsed_time(b) for a, b in kev) / n_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), int(ed.kernel_launch_count() - l0)
-
-    ms, kms, launches = timed(max(1, min(args.warmup, 3)), args.steps)
+    sh = ShardedOperator(ctx, make)
+    ctx.sync()
+    t_setup = time.perf_counter() - t0
+    d = sh.dimension
+    x, y = sh.vector(), sh.vector()
+    x.randn(20260717 + 4, 1.0 / math.sqrt(d))
+    l0 = ed.kernel_launch_count()
+    ms_free = time_sharded(ctx, lambda: sh.apply(y, x), 1, max(2, min(steps, 3)))
+    launches_free = (ed.kernel_launch_count() - l0) // (1 + max(2, min(steps, 3)))
+    dot_free = sh.apply(y, x, dot=True)
     t0 = time.perf_counter()
-    nnz = ropr.cache_matrix()
-    torch.cuda.synchronize()
+    nnz_local = sum(o.cache_matrix() for o in sh.oprs)
+    ctx.sync()
     t_cache = time.perf_counter() - t0
-    ms_c, kms_c, launches_c = timed(3, max(args.steps, 10))
-    nnz_t = torch.tensor([float(nnz)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(nnz_t)
-    nnz_total = int(nnz_t[0])
-    if rank != 0:
-        return
-    peak, src = peaks()
-    alg = 40.0 * n_local                      # SURVEY 8(d): 8 B word + 16 B x + 16 B y per owned row
-    emit({"metric": "H*v matvecs/sec", "value": 1e3 / ms, "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
-                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                      "dtype": "c128", "data": "synthetic", "gnnz_per_s": nnz_total / (ms * 1e-3) / 1e9,
-                      "config": {"workload": name, "description": w["desc"], "dim": d, "parent_dim": hsr.dimension,
-                                 "n_terms": len(h.terms), "rows_per_gpu": n_local, "sharding": "rows" if world > 1 else "none",
-                                 "exchange": "nccl all_gather of x per matvec" if world > 1 else "none",
-                                 "symmetry_reduce_seconds": t_reduce, "kernel": "matrix-free (K6 staged)",
-                                 "l2": "x and y are %.0f MB each, larger than L2; no flush needed" % (d * 16 / 1e6),
-                                 "cached_csr": {"nnz": nnz_total, "assemble_seconds": t_cache, "ms_per_matvec": ms_c, "kernel_ms": kms_c,
-                                                "matvec_per_s": 1e3 / ms_c, "gnnz_per_s": nnz_total / (ms_c * 1e-3) / 1e9,
-                                                "spmv_GBps_per_gpu": (nnz * 12.0 + 48.0 * n_local) / (kms_c * 1e-3) / 1e9,
-                                                "roofline_frac": alg / (kms_c * 1e-3) / 1e9 / peak, "gpu_launches": launches_c},
-                                 "note": "matrix-free path is instruction-bound (432 group images per off-diagonal hit), not HBM-bound (SURVEY H1)"},
-                      "roofline": {"bound": "hbm", "achieved": alg / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                   "frac": alg / (kms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": src, "kernel_ms": kms,
-                                   "algorithmic_bytes_per_launch": alg},
-                      "gpu_launches": launches})
+    nnz = int(ctx.allreduce([float(nnz_local)])[0])
+    ms_csr = time_sharded(ctx, lambda: sh.apply(y, x), 3, max(steps, 10))
+    dot_csr = sh.apply(y, x, dot=True)
+    n_local = sh.info(0)["n_local"]
+    alg = 40.0 * n_local                       # SURVEY 8(d): 8 B word + 16 B x + 16 B y per owned row
+    out = {"workload": "tri6x6_k0A1_sz0", "dim": d, "parent_dim": 9075135300, "n_terms": len(h.terms), "group_order": len(symops),
+           "dtype": "c128", "rows_per_gpu": n_local, "exchange": "none" if ctx.world == 1 else "NCCL all-gather of x per matvec (in-library)",
+           "setup_seconds": t_setup,
+           "matrix_free": {"ms_per_matvec": ms_free, "matvec_per_s": 1e3 / ms_free, "gnnz_per_s": nnz / (ms_free * 1e-3) / 1e9,
+                           "roofline": {"bound": "hbm", "achieved": alg / (ms_free * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": alg / (ms_free * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg},
+                           "gpu_launches": int(launches_free), "kernel": "K6 staged (emit / canonicalize / combine)",
+                           "note": "instruction-bound (orbit search per off-diagonal hit), not HBM-bound (SURVEY H1)"},
+           "cached_csr": {"nnz": nnz, "assemble_seconds": t_cache, "ms_per_matvec": ms_csr, "matvec_per_s": 1e3 / ms_csr,
+                          "gnnz_per_s": nnz / (ms_csr * 1e-3) / 1e9,
+                          "roofline": {"bound": "hbm", "achieved": alg / (ms_csr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": alg / (ms_csr * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg}},
+           "checksum_x_dot_Hx": [dot_free.real, dot_csr.real]}
+    x.close(); y.close(); sh.close()
+    return out
+
+
+def bench_sparse(ed, np):
+    """sparse() assembly times of BASELINE configs 1 and 2 (and L=24 for scale): seconds and nnz/s, device work only"""
+    out = {}
+
+    def timed(opr):
+        opr.sparse_csc()                     # warm-up (allocations, term upload)
+        t0 = time.perf_counter()
+        cp, rv, nz = opr.sparse_csc()
+        return time.perf_counter() - t0, int(cp[-1] - 1)
+
+    hs, h = ed.models.heisenberg_chain(16)
+    dt, nnz = timed(ed.represent(ed.represent(ed.HilbertSpaceSector(hs, 0)), h))
+    out["config1_L16"] = {"seconds": dt, "nnz": nnz, "nnz_per_s": nnz / dt}
+    hs, h = ed.models.heisenberg_square(4, 4)
+    hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
+    t_all, nnz_all = 0.0, 0
+    for k2 in range(4):
+        for k1 in range(4):
+            rhsr = ed.symmetry_reduce(hsr, ed.lattices.torus_translation_irrep(4, 4, k1, k2))
+            dt, nnz = timed(ed.represent(rhsr, h))
+            t_all += dt; nnz_all += nnz
+    out["config2_sq4x4_16_sectors"] = {"seconds": t_all, "nnz": nnz_all, "nnz_per_s": nnz_all / t_all}
+    hs, h = ed.models.xxz_chain(24, 1.0)
+    dt, nnz = timed(ed.represent(ed.represent(ed.HilbertSpaceSector(hs, 0)), h))
+    out["xxz_L24"] = {"seconds": dt, "nnz": nnz, "nnz_per_s": nnz / dt, "includes": "device assembly + 0.7 GB D2H of the CSC arrays"}
+    return out
 
 
 def main():
@@ -281,31 +334,27 @@ def main():
     ap.add_argument("--impl", default="edcuda")
     ap.add_argument("--workload", default="xxz_chain_L32_sz0")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "dma", "allgather"],
-                    help="N>1: how remote rows of x reach a rank: peer loads over NVLink inside the kernel (p2p) or an NCCL all-gather per matvec")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "allgather"],
+                    help="N>1: how remote rows of x reach a rank: halo copies over NVLink (packed by the owner, pulled by copy engines) or an NCCL all-gather per matvec")
+    ap.add_argument("--chunks", type=int, default=0, help="N>1: launch chunks per matvec (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--lanczos", type=int, default=0,
-                    help="also run this many device-resident Lanczos steps (sharded over the ranks) and report ms/step and the lowest Ritz value")
+    ap.add_argument("--no-extras", action="store_true", help="skip the lanczos / tri6x6 / sparse / parity_sample sub-objects")
+    ap.add_argument("--lanczos", type=int, default=100, help="device-resident Lanczos steps for the `lanczos` sub-object (0 = skip)")
     args = ap.parse_args()
     claim_stdout()
-    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     name = args.workload
     w = WORKLOADS[name]
     if args.impl == "reference":
-        if w["kind"] == "tri":
-            # the reference keeps 32 B per PARENT state (9.08e9 states -> 290 GB of maps): not runnable on this host,
-            # and the oracle's C twin only restates the plain-basis apply_parallel!
-            if int(os.environ.get("RANK", "0")) == 0:
-                emit({"impl": "reference", "unavailable": "reference algorithm needs ~360 GB of host memory for the 6x6 triangular parent space (SURVEY 8d); no CPU arm for this workload"})
-            return
         run_reference(args, w, name)
         return
+    args.warmup = max(args.warmup, 3)
 
+    sys.path.insert(0, os.path.join(ROOT, "exactdiagonalization.jl_b200"))
     import numpy as np
     import torch
     import edcuda as ed
-    from edcuda.lanczos import P2PShardedMatvec, ShardedMatvec
+    from edcuda.distributed import Context, ShardedOperator
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,167 +362,184 @@ def main():
     if ed.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; libedcuda has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    from edcuda._lib import lib, check
-    check(lib.ed_set_device(local_rank))
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
+    ctx = Context.from_env()                  # world 1: a trivial context; world > 1: NCCL communicator inside the library
+    peak, peak_src = peaks()
 
     if w["kind"] == "tri":
-        run_reduced(args, w, name, ed, torch, np, rank, world, dev)
-        if world > 1:
-            dist.destroy_process_group()
+        tri = bench_tri6x6(ed, np, ctx, args.steps, peak)
+        if rank == 0:
+            mf = tri["matrix_free"]
+            emit({"metric": "H*v matvecs/sec", "value": mf["matvec_per_s"], "unit": "matvec/s", "n_gpus": world, "steps": args.steps,
+                  "warmup": args.warmup, "ms_per_step": mf["ms_per_matvec"], "higher_is_better": True, "scaling": "strong",
+                  "vs_baseline": None, "dtype": "c128", "data": "synthetic", "gnnz_per_s": mf["gnnz_per_s"],
+                  "config": base_config(name, w), "roofline": dict(mf["roofline"], traffic=None, peak_source=peak_src),
+                  "gpu_launches": mf["gpu_launches"], "tri6x6": tri})
+        ctx.close()
         return
+
     n = w["n"]
-    hs, h, n_bonds = build_model(ed, w)
+    n_bonds = n_bonds_of(w)
+    hs, h = build_model(ed, w)
     hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
     dim = hsr.dimension
-    opr = ed.represent(hsr, h).set_kernel(args.kernel)
-    p2p = world > 1 and args.exchange in ("p2p", "dma") and args.kernel == 0
-    mv = P2PShardedMatvec(opr, rank, world, np.float64, n_buffers=1, exchange=args.exchange) if p2p else ShardedMatvec(opr, rank, world, np.float64)
-    n_local = mv.n_local
-    mv_ranges = list(mv.local_ranges)
-    # synthetic input: Philox normal vector keyed by the global row index (shard-count independent)
-    x_local = mv.x_buffer(0) if p2p else torch.empty(n_local, dtype=torch.float64, device=dev)
-    y_local = torch.zeros(n_local, dtype=torch.float64, device=dev)
-    import ctypes as C
-    check(lib.ed_set_stream(C.c_void_p(torch.cuda.current_stream().cuda_stream), 1))
-    for lo_, hi_, off_ in mv.local_ranges:
-        if hi_ > lo_:
-            check(lib.ed_vector_randn_async(x_local[off_:].data_ptr(), hi_ - lo_, ed.ED_F64, 20260717 + 5, lo_))
-    lib.ed_set_stream(None, 0)
-    x_local.mul_(1.0 / math.sqrt(dim))
-    torch.cuda.synchronize()
+    seed = 20260717 + 5
+    details = {}
+    dev = torch.device("cuda", local_rank)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    if world == 1:
+        # ---- one GPU: the plain C-ABI call (ed_apply_async) on torch's current stream, CUDA events around it
+        import ctypes as C
+        from edcuda._lib import lib, check
+        opr = ed.represent(hsr, h).set_kernel(args.kernel)
+        x = torch.empty(dim, dtype=torch.float64, device=dev)
+        y = torch.zeros(dim, dtype=torch.float64, device=dev)
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib.ed_set_stream(stream, 1))
+        check(lib.ed_vector_randn_async(x.data_ptr(), dim, ed.ED_F64, seed, 0))
+        check(lib.ed_vector_scale_async(x.data_ptr(), dim, ed.ED_F64, 1.0 / math.sqrt(dim)))
+
+        def step():
+            check(lib.ed_apply_async(opr._handle, y.data_ptr(), x.data_ptr(), ed.ED_F64, 0, 0, None))
+
+        for _ in range(args.warmup):
+            step()
         torch.cuda.synchronize()
-
-    def step():
-        if p2p:
-            mv.fence()               # x changed (in a solver): peers may read it only after this stream-ordered barrier
-            mv.matvec(y_local, 0)
-        else:
-            mv.matvec(y_local, x_local)
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+        sampler = ClockSampler(local_rank)
         sampler.start()
-    launches0 = ed.kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev0.record()
-    for i in range(args.steps):
-        if p2p:
-            mv.fence()
-            kev[i][0].record()
-            mv.matvec(y_local, 0)
-            kev[i][1].record()
-            continue
-        if world > 1:
-            xf = mv.gather(x_local)
-        else:
-            xf = x_local          # one GPU owns every row: the local vector is the full vector
-        kev[i][0].record()
-        mv.apply_local(y_local, xf)
-        kev[i][1].record()
-    ev1.record()
-    barrier()
-    launches = ed.kernel_launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev0.elapsed_time(ev1)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kern_ms = float(t[0]), float(t[1])
-    ms_per_step = total_ms / args.steps
+        launches0 = ed.kernel_launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        torch.cuda.synchronize()
+        lib.ed_set_stream(None, 0)
+        launches = ed.kernel_launch_count() - launches0
+        clocks = sampler.stop()
+        ms_per_step = ev0.elapsed_time(ev1) / args.steps
+        kern_ms = ms_per_step                  # one launch per step: the step IS the kernel
+        n_local = dim
+        checksum = float(torch.dot(x, y))
+        details.update({"rows_per_gpu": dim, "sharding": "none", "exchange": "none",
+                        "kernel": "generic term-walk (k2_apply_generic)" if args.kernel == 1 else "tiled U(1) kernel k2_apply_u1"})
+    else:
+        # ---- N GPUs: the library's multi-GPU context end to end
+        sh = ShardedOperator(ctx, lambda: ed.represent(hsr, h).set_kernel(args.kernel), exchange=args.exchange, n_chunks=args.chunks)
+        info = sh.info(0)
+        xv, yv = sh.vector(), sh.vector()
+        xv.randn(seed, 1.0 / math.sqrt(dim))
+        for _ in range(args.warmup):
+            sh.apply(yv, xv)
+        ctx.barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = ed.kernel_launch_count()
+        ctx.timer_record(0)
+        for _ in range(args.steps):
+            sh.apply(yv, xv)
+        ctx.timer_record(1)
+        ms_per_step = ctx.timer_elapsed(0, 1) / args.steps
+        ctx.barrier()
+        launches = ed.kernel_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        kern_ms = ms_per_step
+        n_local = info["n_local"]
+        checksum = sh.apply(yv, xv, dot=True).real
+        halo_max = int(ctx.allreduce([float(info["n_halo"])], "max")[0])
+        details.update({"rows_per_gpu": n_local, "sharding": "tiles assigned by the library's planner (ed_u1_shard_layout)" if info["exchange"] == "halo" else "contiguous row ranges",
+                        "exchange": ("owner-side pack + copy-engine pulls of the packed tiles over NVLink into a halo buffer, %d launch chunks, one NCCL fence per matvec" % info["n_chunks"])
+                        if info["exchange"] == "halo" else "NCCL all-gather of x per matvec", "halo_rows_max": halo_max,
+                        "nvlink_bytes_per_rank_per_matvec_max": halo_max * 8, "pulls_per_matvec": info["n_pulls"],
+                        "nccl_version": ctx.nccl_version, "collectives": "in-library NCCL (no torch.distributed on the data path)",
+                        "kernel": "generic term-walk (k2_apply_generic)" if args.kernel == 1 else "tiled U(1) kernel k2_apply_u1"})
     value = 1e3 / ms_per_step
-    checksum = float(torch.dot(x_local, y_local))   # <x, Hx> partial: a sanity value, not timed
-    if world > 1:
-        cs = torch.tensor([checksum], dtype=torch.float64, device=dev)
-        dist.all_reduce(cs)
-        checksum = float(cs[0])
+    details["checksum_x_dot_Hx"] = checksum
 
-    # ---- e2e: the public call with HOST (pinned) buffers, H2D/D2H inside the timed region --------------
+    # ---- e2e: HOST vectors in and out, H2D / D2H inside the timed region ----------------------------------------
     e2e = None
     if not args.no_e2e:
+        e_steps = max(2, min(args.steps, 5))
         if world == 1:
             xh = torch.empty(dim, dtype=torch.float64).pin_memory()
-            yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
-            xh.copy_(x_local)
+            yh = torch.empty(dim, dtype=torch.float64).pin_memory()
+            xh.copy_(x)
             xn, yn = xh.numpy(), yh.numpy()
-            e_steps = max(2, min(args.steps, 5))
-            ed.mul_b(yn, opr, xn)   # warm-up (allocations)
+            ed.mul_b(yn, opr, xn)             # warm-up (staging allocations)
             t0 = time.perf_counter()
             for _ in range(e_steps):
                 ed.mul_b(yn, opr, xn)
             dt = (time.perf_counter() - t0) / e_steps
             assert abs(float(np.dot(xn, yn)) - checksum) <= 1e-9 * max(1.0, abs(checksum))
-            e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(n_local * 8),
+            e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(dim * 8),
                    "ms_per_step": dt * 1e3, "api": "edcuda.mul_b(out, opr, x) = mul!(out, opr, x) with pinned host vectors -> ed_apply"}
         else:
-            # every rank holds its rows of x and y in pinned host memory; a step = H2D of the local x rows,
-            # NCCL all-gather, local apply, D2H of the local y rows
+            # every rank keeps its rows of x and y in pinned host memory; a step = H2D of its x rows, the sharded matvec, D2H of its y rows
+            st = torch.cuda.ExternalStream(ctx.stream(0), device=dev)
+            xt, yt = xv.tensor(0), yv.tensor(0)
             xh = torch.empty(n_local, dtype=torch.float64).pin_memory()
             yh = torch.empty(n_local, dtype=torch.float64).pin_memory()
-            xh.copy_(x_local)
-            xd = x_local if p2p else torch.empty_like(x_local)
-            e_steps = max(2, min(args.steps, 5))
-            barrier()
+            with torch.cuda.stream(st):
+                xh.copy_(xt)
+            ctx.barrier()
             t0 = time.perf_counter()
             for _ in range(e_steps):
-                xd.copy_(xh, non_blocking=True)
-                if p2p:
-                    mv.fence()
-                    mv.matvec(y_local, 0)
-                else:
-                    mv.matvec(y_local, xd)
-                yh.copy_(y_local, non_blocking=True)
-                torch.cuda.synchronize()
-            barrier()
-            dt = (time.perf_counter() - t0) / e_steps
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt[0])
+                with torch.cuda.stream(st):
+                    xt.copy_(xh, non_blocking=True)
+                sh.apply(yv, xv)
+                with torch.cuda.stream(st):
+                    yh.copy_(yt, non_blocking=True)
+                ctx.sync()
+            ctx.barrier()
+            dt = float(ctx.allreduce([(time.perf_counter() - t0) / e_steps], "max")[0])
             e2e = {"value": 1.0 / dt, "unit": "matvec/s", "h2d_bytes_per_step": int(dim * 8), "d2h_bytes_per_step": int(dim * 8),
-                   "ms_per_step": dt * 1e3, "api": ("P2PShardedMatvec" if p2p else "ShardedMatvec") + ".matvec with per-rank pinned host shards (H2D + exchange + ed_apply_async + D2H)"}
+                   "ms_per_step": dt * 1e3, "api": "ed_apply_sharded with per-rank pinned host shards (H2D of the owned rows + pack/pull exchange + kernel + D2H)"}
+            del xh, yh
 
-    # ---- optional: K7 Lanczos loop on the same representation (config 5 of BASELINE.json) -----------------------
-    lanczos_info = None
-    p2p_used = p2p
-    if args.lanczos > 0:
-        from edcuda.lanczos import ShardedLanczos
-        if p2p:
-            mv.close()
-        del mv
+    extras = {}
+    if not args.no_extras:
+        # ---- parity of the timed output against the oracle's C twin (N=1: sampled rows of the same x) ------------
+        cpu = None
+        if world == 1 and w["kind"] in ("xxz", "j1j2"):
+            xh_np = xh.numpy() if not args.no_e2e else x.cpu().numpy()
+            cpu = CpuReference(w, x=xh_np)
+            half = math.comb(n - 1, n // 2)
+            blocks = sorted({(max(0, lo), min(dim, lo + 20000)) for lo in (0, dim - 20000, half - 10000, dim // 2, dim // 3, (1 << 29) - 10000 if dim > (1 << 29) + 10000 else dim // 5)})
+            extras["parity_sample"] = cpu.parity(lambda lo, hi: y[lo:hi].cpu().numpy(), blocks)
+            if not args.no_cpu_baseline:
+                extras["cpu_baseline"] = cpu.sample(12.0)
+            del cpu
+        # ---- config 5: device-resident Lanczos on the same representation -------------------------------------
+        if args.lanczos > 0:
+            if world == 1:
+                del x, y
+                if e2e is not None:
+                    del xh, yh, xn, yn
+                ed._lib.lib.ed_release_staging()
+                torch.cuda.empty_cache()
+                sh = ShardedOperator(ctx, lambda: opr)
+            else:
+                xv.close(); yv.close()
+            sh.lanczos(3, seed=1)            # warm-up
+            res = sh.lanczos(args.lanczos, seed=20260717)
+            extras["lanczos"] = {"steps": int(res.steps), "ms_per_step": res.ms_per_step, "lowest_ritz": float(res.ritz[0]) if len(res.ritz) else None,
+                                 "e0_per_site_over_4": (float(res.ritz[0]) / (4.0 * n)) if len(res.ritz) else None,
+                                 "api": "ed_lanczos_sharded (in-library loop; scalars all-reduced over NCCL at N>1)",
+                                 "note": "three-term Lanczos, unnormalised device-resident Krylov vectors, fused <u,Hu> and update+norm kernels"}
+            sh.close()
         torch.cuda.empty_cache()
-        sl = ShardedLanczos(ed.represent(hsr, h).set_kernel(args.kernel), rank, world, np.float64,
-                            exchange=args.exchange if (world > 1 and args.exchange in ("p2p", "dma") and args.kernel == 0) else "allgather")
-        sl.run(3, seed=1)            # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        res = sl.run(args.lanczos, seed=20260717)
-        barrier()
-        dt = time.perf_counter() - t0
-        lanczos_info = {"steps": int(res.steps), "ms_per_step": 1e3 * dt / max(1, args.lanczos), "lowest_ritz": float(res.ritz[0]) if len(res.ritz) else None,
-                        "e0_per_site_over_4": (float(res.ritz[0]) / (4.0 * n)) if len(res.ritz) else None,
-                        "note": "three-term Lanczos, unnormalised device-resident Krylov vectors, fused <u,Hu> and update+norm kernels; scalars all-reduced over NCCL"}
-        if sl.p2p:
-            sl.mv.close()
-        p2p = False
+        # ---- config 4 (6x6 triangular) and sparse() assembly -------------------------------------------------------
+        if name == "xxz_chain_L32_sz0":
+            hsr = None
+            extras["tri6x6"] = bench_tri6x6(ed, np, ctx, args.steps, peak)
+            if world == 1:
+                extras["sparse"] = bench_sparse(ed, np)
+
     if rank == 0:
-        peak, peak_src = peaks()
         alg_bytes = 24.0 * n_local     # 8 B basis word + 8 B x + 8 B y per owned row
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
         if world == 1 and args.kernel == 0 and os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get(name, {}).get("dram_bytes_per_launch")
@@ -482,33 +548,23 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "gnnz_per_s": nnz_eff(n, n_bonds) * value / 1e9,
-            "config": {"workload": name, "description": w["desc"], "n_sites": n, "dim": dim, "n_terms": len(h.terms),
-                       "rows_per_gpu": n_local, "sharding": ("rows" if world > 1 else "none") + (", two wrap-aware ranges per rank" if len(mv_ranges) > 1 else ""),
-                       "exchange": ("none" if world == 1 else
-                                    "split: copy engines pull the needed peer rows into a mirror vector during a rank-local kernel pass, a second pass adds them (CUDA IPC), "
-                                    "stream-ordered NCCL fence per matvec" if (p2p_used and args.exchange == "dma") else
-                                    "peer loads of far-bond tiles over NVLink inside the kernel (CUDA IPC), "
-                                    "stream-ordered NCCL fence per matvec" if p2p_used else "nccl all_gather of x per matvec"),
-                       "l2": "inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (dim * 8 / 1e9),
-                       "kernel": "generic term-walk" if args.kernel == 1 else "auto",
-                       "checksum_x_dot_Hx": checksum},
+            "config": dict(base_config(name, w)),
+            "details": dict(details, l2="inputs larger than L2 (x and y are %.2f GB each per GPU); no flush needed" % (n_local * 8 / 1e9)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": "ncu --set full capture committed under profiles/ (bytes per launch)" if traffic else None,
-                         "peak_source": peak_src, "kernel_ms": kern_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "frac_of_nominal_8TBs": achieved / 8000.0},
+                         "peak_source": peak_src, "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "bytes_definition": "SURVEY 8(d): (8 B basis word + 8 B x + 8 B y) per owned row",
+                         "frac_of_vector_bytes_only": 16.0 * n_local / (kern_ms * 1e-3) / 1e9 / peak,
+                         "vector_bytes_note": "the tiled kernel reads no basis word (combinatorial ranks): 16 B/row is what it must move",
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if e2e is not None:
             line["e2e"] = e2e
-        if lanczos_info is not None:
-            line["lanczos"] = lanczos_info
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(w)
+        for k, v in extras.items():
+            line[k] = v
         emit(line)
-    if p2p:
-        mv.close()
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 if __name__ == "__main__":

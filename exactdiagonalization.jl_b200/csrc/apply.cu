@@ -122,7 +122,7 @@ void ed_upload_terms(ed_oprep* o) {
 }
 
 static DevBuf<double>& dot_scratch(int n_blocks) {
-  static thread_local DevBuf<double> buf;
+  DevBuf<double>& buf = ed_scratch<double, 1>();
   if (buf.n < (size_t)2 * n_blocks) buf.alloc((size_t)2 * n_blocks);
   return buf;
 }

@@ -34,7 +34,6 @@ void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
 #define U1_MAX_MX 64
 #define U1_MAX_MQ 64
 #define U1_MAX_MS 16
-#define ED_MAX_SEG 16
 
 // Everything that depends only on the LOW k bits of a row is tabulated once per plan (tables live in L2):
 //   dcode / dval   diagonal of the low-bit terms (u8 code -> value)
@@ -71,47 +70,38 @@ struct U1Params {
   int64_t row_lo, row_hi;
   int accumulate;
   int tile_first;               // first tile of the launch (row shards launch only the tiles they overlap)
-  // split exchange (multi-GPU): stream_mode 1 = LOCAL pass (neighbour streams whose tile lives in a peer segment are
-  // skipped), 2 = REMOTE pass (only those streams, read from `mirror` -- a full-length local vector whose needed remote
-  // rows were filled by copy engines meanwhile -- and added to y); 0 = everything in one pass through the segments
+  int partial_first;            // slot of the launch's first tile in the <x,Hx> partials (chunked sharded launches)
+  // Sharded (multi-GPU) launches.  stream_mode 0 = everything in one pass; 1 = LOCAL pass (neighbour tiles that live in
+  // the halo buffer are skipped); 2 = REMOTE pass (only those, added to y).
   int stream_mode;
-  uint32_t local_seg_mask;      // bit s: segment s is this rank's own memory
-  const void* mirror;
   int far_bit;                  // bonds whose upper H bit is >= far_bit read their neighbour tile with evict-first loads:
                                 // its re-use distance (2^(bit+1) tiles) exceeds the L2, so the line is a one-shot
 
   const uint32_t* tile_order;   // optional launch order (whole-basis launches): position -> index into tile_H
-  // x as up to ED_MAX_SEG contiguous, tile-aligned segments (local memory or peer GPUs' memory mapped over NVLink)
-  int n_seg;
-  int64_t seg_lo[ED_MAX_SEG + 1];
-  const void* seg_ptr[ED_MAX_SEG];
+  // Where x lives.  Plain: x_local is the full vector, tile H starts at tile_base[H].  Sharded: `dir[H]` is the element
+  // offset of tile H inside x_local (this rank's own tiles, concatenated) or, with U1_DIR_HALO set, inside x_halo (a
+  // compact buffer holding copies of the peer tiles this rank reads, filled by copy engines over NVLink); -1 = never read.
+  const int64_t* dir;
+  const void* x_local;
+  const void* x_halo;
 };
 
-template <typename VecT>
-__device__ __forceinline__ const VecT* u1_seg_resolve(const U1Params& P, uint64_t idx) {
-  int s = 0;
-  while (s + 1 < P.n_seg && (int64_t)idx >= P.seg_lo[s + 1]) ++s;
-  return reinterpret_cast<const VecT*>(P.seg_ptr[s]) + ((int64_t)idx - P.seg_lo[s]);
-}
+#define U1_DIR_HALO (1ll << 62)
 
+// neighbour tile H2 under the exchange mode: false = this pass does not read it
 template <typename VecT>
-__device__ __forceinline__ const VecT* u1_seg_resolve(const U1Params& P, uint64_t idx, int& seg) {
-  int s = 0;
-  while (s + 1 < P.n_seg && (int64_t)idx >= P.seg_lo[s + 1]) ++s;
-  seg = s;
-  return reinterpret_cast<const VecT*>(P.seg_ptr[s]) + ((int64_t)idx - P.seg_lo[s]);
-}
-
-// neighbour tile starting at global row `idx` under the exchange mode: false = this pass does not read it
-template <typename VecT>
-__device__ __forceinline__ bool u1_neighbour(const U1Params& P, uint64_t idx, const VecT*& ptr) {
-  int seg;
-  ptr = u1_seg_resolve<VecT>(P, idx, seg);
-  if (P.stream_mode == 0) return true;
-  const bool local = (P.local_seg_mask >> seg) & 1u;
-  if (P.stream_mode == 1) return local;
-  ptr = reinterpret_cast<const VecT*>(P.mirror) + idx;
-  return !local;
+__device__ __forceinline__ bool u1_neighbour(const U1Params& P, uint32_t H2, const VecT*& ptr) {
+  if (!P.dir) {
+    ptr = reinterpret_cast<const VecT*>(P.x_local) + P.tile_base[H2];
+    return true;
+  }
+  const int64_t e = P.dir[H2];
+  if (e < 0) return false;
+  const bool halo = (e & U1_DIR_HALO) != 0;
+  if (P.stream_mode == 1 && halo) return false;
+  if (P.stream_mode == 2 && !halo) return false;
+  ptr = reinterpret_cast<const VecT*>(halo ? P.x_halo : P.x_local) + (e & (U1_DIR_HALO - 1));
+  return true;
 }
 
 struct FastU1Plan {
@@ -131,6 +121,10 @@ struct FastU1Plan {
   std::vector<DevBuf<uint8_t>> ell_cnt;
   DevBuf<double> partials;
   std::vector<uint64_t> h_base, h_size;  // per non-empty tile, ascending
+  // host copies of what the shard planner needs (ed_u1_shard_layout works without a device)
+  std::vector<uint32_t> h_tile_H;
+  std::vector<uint8_t> h_hh_p, h_hh_q, h_mx_q, h_ms_q;
+  int n_hh = 0, n_mx = 0, n_ms = 0, k = 0;
   bool order_on = false;
   bool wraps = false;       // a tabulated straddler flips the top site (the periodic bond of a ring)
   int hb = 0;               // bits of H
@@ -431,7 +425,8 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   const int p_low = P.n_set - __popc(H);
   const uint32_t lofs = P.lowofs[p_low];
   const uint32_t size = P.lowofs[p_low + 1] - lofs;
-  const uint64_t base = P.tile_base[H];
+  // position of the tile in x_local (and, minus row_lo, in y): its global rank, or its slot in this rank's shard
+  const int64_t base = P.dir ? P.dir[H] : (int64_t)P.tile_base[H];
   const int k = P.k;
 
   // ---- prologue: per-tile bond lists (deterministic ballot compaction), x tile --------------------------
@@ -447,7 +442,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
         H2 = H ^ ((1u << p) | (1u << q));
       }
       const VecT* xn = nullptr;
-      if (fire) fire = u1_neighbour<VecT>(P, P.tile_base[H2], xn);
+      if (fire) fire = u1_neighbour<VecT>(P, H2, xn);
       const unsigned m = __ballot_sync(0xffffffffu, fire);
       if (fire) {
         const int slot = n + __popc(m & ((1u << tid) - 1u));
@@ -465,7 +460,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       bool on = b < P.n_mx;
       const VecT* xn = nullptr;
       int q = 0;
-      if (on) { q = P.mx_q[b]; on = u1_neighbour<VecT>(P, P.tile_base[H ^ (1u << q)], xn); }
+      if (on) { q = P.mx_q[b]; on = u1_neighbour<VecT>(P, H ^ (1u << q), xn); }
       const unsigned m = __ballot_sync(0xffffffffu, on);
       if (on) {
         const int slot = n + __popc(m & ((1u << lane) - 1u));
@@ -483,7 +478,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       bool on = b < P.n_ms;
       const VecT* xn = nullptr;
       int q = 0;
-      if (on) { q = P.ms_q[b]; on = u1_neighbour<VecT>(P, P.tile_base[H ^ (1u << q)], xn); }
+      if (on) { q = P.ms_q[b]; on = u1_neighbour<VecT>(P, H ^ (1u << q), xn); }
       const unsigned m = __ballot_sync(0xffffffffu, on);
       if (on) {
         const int slot = n + __popc(m & ((1u << lane) - 1u));
@@ -529,12 +524,12 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   if (P.stream_mode == 2) {                             // remote pass: most tiles have nothing to add
     __syncthreads();
     if (s_counts[0] + s_counts[2] + s_counts[3] == 0) {
-      if (dot_partials && tid == 0) { dot_partials[2 * blockIdx.x] = 0.0; dot_partials[2 * blockIdx.x + 1] = 0.0; }
+      if (dot_partials && tid == 0) { dot_partials[2 * (P.partial_first + blockIdx.x)] = 0.0; dot_partials[2 * (P.partial_first + blockIdx.x) + 1] = 0.0; }
       return;
     }
   }
   {
-    const VecT* xo = u1_seg_resolve<VecT>(P, base);     // segments are tile aligned: the whole tile is in one segment
+    const VecT* xo = reinterpret_cast<const VecT*>(P.x_local) + base;
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
   }
   if (tid == 0) xs[size] = vzero((VecT*)nullptr);
@@ -547,7 +542,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   T.ms_amp = ms_amp; T.ms_ptr = ms_ptr; T.ms_lo = ms_lo; T.ms_len = ms_len; T.n_ms = s_counts[3];
   T.mq_coef = mq_coef; T.mq_bit = mq_bit; T.n_mq = s_counts[1];
   T.s_dval = s_dval;
-  T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = (int64_t)base;
+  T.lofs = lofs; T.gofs = P.grpofs[p_low]; T.size = size; T.p_low = p_low; T.base = base;
   T.d_tile = P.tile_diag[H];
   double dre = 0.0, dim_ = 0.0;
   // passes of at most R slabs (R accumulators per thread stay in registers); all slabs but the very last are complete
@@ -567,8 +562,8 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
     if (tid == 0) {
       double a = 0, c = 0;
       for (int w = 0; w < THREADS / 32; ++w) { a += s_red[0][w]; c += s_red[1][w]; }
-      dot_partials[2 * blockIdx.x] = a;
-      dot_partials[2 * blockIdx.x + 1] = c;
+      dot_partials[2 * (P.partial_first + blockIdx.x)] = a;
+      dot_partials[2 * (P.partial_first + blockIdx.x) + 1] = c;
     }
   }
 }
@@ -668,14 +663,12 @@ int choose_k(int n_bits, int vec_bytes) {
 
 }  // namespace
 
-static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
+// host_only: everything except the device uploads (shard planning and its CPU tests need no GPU)
+static std::shared_ptr<FastU1Plan> build_plan(const ed_operator& op, int n_bits, int n_set, int vec_bytes, bool host_only) {
   auto plan = std::make_shared<FastU1Plan>();
-  ed_basis* b = o->basis;
   plan->vec_bytes = vec_bytes;
-  if (b->kind != ED_BASIS_COMBINADIC || b->dim <= 0) return plan;
-  const int n_bits = b->space.bits, n_set = b->n_set;
-  if (n_bits < 1 || n_bits > 42) return plan;
-  Lowered L = lower_operator(o->op, n_bits, n_set);
+  if (n_bits < 1 || n_bits > 42 || n_set < 0 || n_set > n_bits) return plan;
+  Lowered L = lower_operator(op, n_bits, n_set);
   if (!L.ok) return plan;
   const int k = choose_k(n_bits, vec_bytes);
   const int hb = n_bits - k;
@@ -683,7 +676,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   U1Params& P = plan->P;
   memset(&P, 0, sizeof(P));
   P.n_bits = n_bits; P.n_set = n_set; P.k = k;
-  plan->idx32 = b->dim < (1ll << 32);
+  plan->idx32 = binom_u64(n_bits, n_set) < (1ull << 32);
   const uint32_t nlow = 1u << k;
   const uint32_t nH = 1u << hb;
   const uint64_t lowmask = (1ull << k) - 1ull;
@@ -887,8 +880,10 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
           }
       }
       if (table.empty()) table.push_back(0);
-      plan->ell[c].upload(table);
-      plan->ell_cnt[c].upload(cnt);
+      if (!host_only) {
+        plan->ell[c].upload(table);
+        plan->ell_cnt[c].upload(cnt);
+      }
       ++c;
     }
   }
@@ -921,6 +916,16 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   }
   P.tile_cap = tile_cap;
   plan->n_tiles = (int)tile_H.size();
+  plan->k = k; plan->n_hh = P.n_hh; plan->n_mx = P.n_mx; plan->n_ms = P.n_ms;
+  plan->h_tile_H = tile_H;
+  plan->h_hh_p = hh_p; plan->h_hh_q = hh_q; plan->h_mx_q = mx_q; plan->h_ms_q = ms_q;
+  plan->hb = hb;
+  plan->wraps = false;
+  for (int e = 0; e < P.n_mx; ++e) plan->wraps |= (int)mx_q[e] == hb - 1;
+  if (host_only) {
+    plan->supported = true;
+    return plan;
+  }
   {
     int dev = 0, l2 = 0;
     ED_CUDA(cudaGetDevice(&dev));
@@ -929,25 +934,7 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
     P.far_bit = 0;
     while (P.far_bit < hb && std::ldexp(tile_bytes, P.far_bit + 1) <= (double)l2) ++P.far_bit;
   }
-  // optional launch order for whole-basis launches: tiles grouped by a window of "slow" H bits, so that the tiles
-  // running at the same time are closed under the bonds on the remaining (fast) bits -- including the periodic bond,
-  // whose H bit is the top one -- and find each other's x in L2.  EDCUDA_U1_ORDER="first_slow_bit,n_slow_bits".
   plan->order_on = false;
-  if (const char* e = getenv("EDCUDA_U1_ORDER")) {
-    int s0 = -1, ns = 0;
-    if (sscanf(e, "%d,%d", &s0, &ns) == 2 && s0 >= 0 && ns > 0 && s0 + ns <= hb) {
-      std::vector<uint32_t> order(tile_H.size());
-      for (size_t i = 0; i < order.size(); ++i) order[i] = (uint32_t)i;
-      const uint32_t smask = ((1u << ns) - 1u) << s0;
-      std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return (tile_H[a] & smask) < (tile_H[b] & smask); });
-      plan->tile_order.upload(order);
-      plan->order_on = true;
-    }
-  }
-
-  plan->hb = hb;
-  plan->wraps = false;
-  for (int e = 0; e < P.n_mx; ++e) plan->wraps |= (int)mx_q[e] == hb - 1;
 
   auto nonempty8 = [](std::vector<uint8_t>& v) { if (v.empty()) v.push_back(0); };
   auto nonemptyd = [](std::vector<double>& v) { if (v.empty()) v.push_back(0.0); };
@@ -980,10 +967,17 @@ static std::shared_ptr<FastU1Plan> build_plan(ed_oprep* o, int vec_bytes) {
   return plan;
 }
 
+static void u1_apply_env_order(FastU1Plan* plan);
+
 static FastU1Plan* get_plan(ed_oprep* o, int dtype) {
   // one plan per vector type (the tile size depends on the element size), cached on the representation
   std::shared_ptr<FastU1Plan>& slot = dtype == ED_C128 ? o->u1plan_c : o->u1plan;
-  if (!slot) slot = build_plan(o, dtype == ED_C128 ? 16 : 8);
+  if (!slot) {
+    ed_basis* b = o->basis;
+    if (b->kind != ED_BASIS_COMBINADIC || b->dim <= 0) slot = std::make_shared<FastU1Plan>();
+    else slot = build_plan(o->op, b->space.bits, b->n_set, dtype == ED_C128 ? 16 : 8, false);
+    if (slot->supported) u1_apply_env_order(slot.get());
+  }
   return slot.get();
 }
 
@@ -1000,155 +994,362 @@ constexpr int U1_THREADS = 512;
 template <typename VecT, int R>
 static void launch_u1(FastU1Plan* plan, const U1Params& P, int n_launch, void* out, double* partials) {
   auto kern = k2_apply_u1<VecT, U1_THREADS, R>;
-  static thread_local size_t configured = 0;
-  if (plan->smem_bytes > 48 * 1024 && configured < plan->smem_bytes) {
+  static size_t configured[64] = {0};   // per device: the opt-in shared-memory size is a per-device function attribute
+  int dev = 0;
+  ED_CUDA(cudaGetDevice(&dev));
+  if (plan->smem_bytes > 48 * 1024 && configured[dev & 63] < plan->smem_bytes) {
     ED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem_bytes));
-    configured = plan->smem_bytes;
+    configured[dev & 63] = plan->smem_bytes;
   }
   ED_LAUNCH(kern, n_launch, U1_THREADS, plan->smem_bytes, P, reinterpret_cast<VecT*>(out), partials);
 }
 
-// contiguous, count-balanced row ranges whose boundaries fall on tile boundaries (so every tile, and therefore every
-// neighbour stream, lives in exactly one x segment)
+FastU1Plan* ed_u1_plan(ed_oprep* o, int dtype) {
+  FastU1Plan* plan = get_plan(o, dtype);
+  return plan->supported ? plan : nullptr;
+}
+
+std::shared_ptr<FastU1Plan> ed_u1_host_plan(const ed_operator& op, int n_bits, int n_set, int dtype) {
+  return build_plan(op, n_bits, n_set, dtype == ED_C128 ? 16 : 8, true);
+}
+
+// contiguous, count-balanced row ranges whose boundaries fall on tile boundaries
+static int64_t u1_snap(const FastU1Plan* plan, int64_t dim, int64_t target) {
+  if (target <= 0) return 0;
+  if (target >= dim) return dim;
+  if (!plan->supported) return target;
+  auto it = std::lower_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)target);
+  int64_t up = it == plan->h_base.end() ? dim : (int64_t)*it;
+  int64_t down = it == plan->h_base.begin() ? 0 : (int64_t)*(it - 1);
+  return (up - target <= target - down) ? up : down;
+}
+
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi) {
   FastU1Plan* plan = get_plan(o, dtype);
   const int64_t dim = o->dim;
-  auto snap = [&](int64_t target) -> int64_t {
-    if (target <= 0) return 0;
-    if (target >= dim) return dim;
-    if (!plan->supported) return target;
-    auto it = std::lower_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)target);
-    int64_t up = it == plan->h_base.end() ? dim : (int64_t)*it;
-    int64_t down = it == plan->h_base.begin() ? 0 : (int64_t)*(it - 1);
-    return (up - target <= target - down) ? up : down;
-  };
-  *lo = snap(dim / world * rank + std::min<int64_t>(rank, dim % world));
-  *hi = snap(dim / world * (rank + 1) + std::min<int64_t>(rank + 1, dim % world));
+  *lo = u1_snap(plan, dim, dim / world * rank + std::min<int64_t>(rank, dim % world));
+  *hi = u1_snap(plan, dim, dim / world * (rank + 1) + std::min<int64_t>(rank + 1, dim % world));
 }
 
-// Wrap-aware shards.  With contiguous single ranges the bond that wraps around the top site (periodic bond of a ring)
-// always lands on another rank, as an 8-byte gather that wastes half of every NVLink sector.  Giving every rank the
-// SAME range of the remaining high bits in both halves of the basis (top site empty / occupied) keeps that bond local:
-// two tile-aligned row ranges per rank, balanced by their combined row count.  Returns 2 ranges, or 1 (the plain
-// split) when the operator has no such bond or the world is too large for the tile grid.
-int ed_u1_suggest_rows2(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi) {
-  FastU1Plan* plan = get_plan(o, dtype);
+// ------------------------------------------------------------------ shard layout (host only)
+// Which rank owns which tile, and what moves between ranks per matvec.
+//
+// A rank reads, besides its own tiles, every tile H' = bond(H) of its tiles H (about 10 per tile at L=32).  Tiles are
+// assigned by cutting an ORDERING of all tiles into `world` pieces of equal row count, so the volume a rank must fetch
+// ("halo") is the boundary of its piece.  Candidate orderings:
+//   * ascending H -- contiguous row ranges, the reference's splitrange (util.jl:102-121) snapped to tiles; when a bond
+//     wraps around the most significant site, with the top bit as the LEAST significant key (every rank owns the same
+//     range of the remaining bits in both halves of the basis, which keeps the wrapping bond local);
+//   * popcount keys: the high bits are split into one or two contiguous blocks and tiles are ordered by the number of
+//     particles in each block (boustrophedon), then by the block bits.  A bond inside a block keeps the popcounts, so
+//     only the few bonds at the block boundaries leave a class: at L=32 the largest halo drops from 2.3e8 to 1.0e8 rows
+//     at 8 ranks and from 2.3e8 to 0.8e8 rows at 2 ranks.
+// The planner evaluates every candidate on the actual bond lists (any lattice) and keeps the one with the smallest
+// maximum halo (policy 0).  policy 1 = plain ascending ranges; 2 = wrap-aware ranges; 3 = best popcount key.
+namespace {
+
+struct U1Global {
+  int world = 1, n_chunks = 1;
+  std::string key_name;
+  std::vector<int> owner;                       // [tile]
+  std::vector<int64_t> off;                     // [tile] offset in its owner's local vectors (ascending-H storage)
+  std::vector<int64_t> rows_of_rank;
+  std::vector<std::vector<uint32_t>> launch;    // [rank] tile indices in launch order (the key's order)
+  std::vector<std::vector<int>> chunk_first;    // [rank][n_chunks + 1]
+  // halo of rank r: tile indices in halo order = (chunk, owner, tile) ascending
+  std::vector<std::vector<uint32_t>> halo_tiles;
+  std::vector<std::vector<int>> halo_chunk;     // chunk of every halo tile
+  std::vector<int64_t> exch;                    // [(p * world + r) * n_chunks + c] rows sent p -> r for chunk c
+  int64_t send_off(int p, int r, int c) const {  // offset of that segment in p's send buffer: receiver-major, then chunk
+    int64_t o = 0;
+    for (int r2 = 0; r2 < r; ++r2) for (int c2 = 0; c2 < n_chunks; ++c2) o += exch[((size_t)p * world + r2) * n_chunks + c2];
+    for (int c2 = 0; c2 < c; ++c2) o += exch[((size_t)p * world + r) * n_chunks + c2];
+    return o;
+  }
+};
+
+struct TileGraph {
+  size_t nt = 0;
+  int hb = 0;
+  std::vector<int32_t> index_of;                // [2^hb]
+  std::vector<int32_t> nbr;                     // [nt * deg] neighbour tile index or -1
+  int deg = 0;
+};
+
+TileGraph u1_tile_graph(const FastU1Plan* plan) {
+  TileGraph G;
+  G.nt = plan->h_tile_H.size();
+  G.hb = plan->hb;
+  G.index_of.assign((size_t)1 << G.hb, -1);
+  for (size_t t = 0; t < G.nt; ++t) G.index_of[plan->h_tile_H[t]] = (int32_t)t;
+  G.deg = plan->n_hh + plan->n_mx + plan->n_ms;
+  G.nbr.assign(G.nt * (size_t)std::max(G.deg, 1), -1);
+  for (size_t t = 0; t < G.nt; ++t) {
+    const uint32_t H = plan->h_tile_H[t];
+    int32_t* row = G.nbr.data() + t * G.deg;
+    int d = 0;
+    for (int b = 0; b < plan->n_hh; ++b, ++d)
+      if (((H >> plan->h_hh_p[b]) ^ (H >> plan->h_hh_q[b])) & 1u) row[d] = G.index_of[H ^ ((1u << plan->h_hh_p[b]) | (1u << plan->h_hh_q[b]))];
+    for (int b = 0; b < plan->n_mx; ++b, ++d) row[d] = G.index_of[H ^ (1u << plan->h_mx_q[b])];
+    for (int b = 0; b < plan->n_ms; ++b, ++d) row[d] = G.index_of[H ^ (1u << plan->h_ms_q[b])];
+  }
+  return G;
+}
+
+// cut an ordering of the tiles into `world` pieces of (nearly) equal row count
+void u1_cut(const FastU1Plan* plan, const std::vector<uint32_t>& order, int world, std::vector<int>& owner) {
+  uint64_t total = 0;
+  for (uint64_t v : plan->h_size) total += v;
+  owner.assign(order.size(), 0);
+  uint64_t acc = 0;
+  for (uint32_t t : order) {
+    // piece of the tile's midpoint: tiles never straddle, the pieces differ by at most one tile
+    const uint64_t mid = acc + plan->h_size[t] / 2;
+    owner[t] = (int)std::min<uint64_t>((unsigned __int128)mid * (uint64_t)world / std::max<uint64_t>(total, 1), (uint64_t)world - 1);
+    acc += plan->h_size[t];
+  }
+}
+
+// largest halo (rows of distinct peer tiles read) over the ranks
+uint64_t u1_max_halo(const FastU1Plan* plan, const TileGraph& G, const std::vector<int>& owner, int world) {
+  std::vector<std::vector<uint32_t>> by_rank(world);
+  for (size_t t = 0; t < G.nt; ++t) by_rank[owner[t]].push_back((uint32_t)t);
+  std::vector<int32_t> stamp(G.nt, -1);         // last rank that counted the tile: ranks are swept one after the other
+  uint64_t worst = 0;
+  for (int r = 0; r < world; ++r) {
+    uint64_t halo = 0;
+    for (uint32_t t : by_rank[r]) {
+      const int32_t* row = G.nbr.data() + (size_t)t * G.deg;
+      for (int d = 0; d < G.deg; ++d) {
+        const int32_t j = row[d];
+        if (j < 0 || owner[j] == r || stamp[j] == r) continue;
+        stamp[j] = r;
+        halo += plan->h_size[j];
+      }
+    }
+    worst = std::max(worst, halo);
+  }
+  return worst;
+}
+
+struct KeySpec { std::string name; int kind; int a0, s, b1; };   // kind 0 plain, 1 wrap ranges, 2 popcount blocks [a0,s)[s,b1) (s<0: one block)
+
+void u1_order_by_key(const FastU1Plan* plan, const KeySpec& K, std::vector<uint32_t>& order) {
+  const size_t nt = plan->h_tile_H.size();
   const int hb = plan->hb;
-  if (!plan->supported || !plan->wraps || hb < 2 || world < 2 || (1 << (hb - 1)) < 4 * world || getenv("EDCUDA_U1_NOWRAPSHARD")) {
-    ed_u1_suggest_rows(o, dtype, world, rank, lo, hi);
-    return 1;
+  std::vector<uint64_t> key(nt);
+  auto maskof = [](int a, int b) -> uint32_t { return b <= a ? 0u : (uint32_t)((((uint64_t)1 << b) - 1) & ~(((uint64_t)1 << a) - 1)); };
+  for (size_t t = 0; t < nt; ++t) {
+    const uint32_t H = plan->h_tile_H[t];
+    if (K.kind == 0) key[t] = H;
+    else if (K.kind == 1) key[t] = ((uint64_t)(H & ((1u << (hb - 1)) - 1u)) << 1) | (H >> (hb - 1));
+    else {
+      const uint32_t m_lo = K.s < 0 ? 0u : maskof(K.a0, K.s), m_hi = K.s < 0 ? maskof(K.a0, K.b1) : maskof(K.s, K.b1);
+      const uint32_t q_hi = (uint32_t)__builtin_popcount(H & m_hi), q_lo = (uint32_t)__builtin_popcount(H & m_lo);
+      const uint32_t w_lo = (uint32_t)__builtin_popcount(m_lo);
+      const uint32_t snake = (q_hi & 1u) ? w_lo - q_lo : q_lo;         // boustrophedon through the lower block
+      key[t] = ((uint64_t)q_hi << 56) | ((uint64_t)snake << 48) | ((uint64_t)(H & (m_lo | m_hi)) << 20) | (uint64_t)(H & ~(m_lo | m_hi) & 0xFFFFFu);
+    }
   }
-  const U1Params& P = plan->P;
-  const uint32_t top = 1u << (hb - 1);
-  auto tile_rows = [&](uint32_t H) -> uint64_t {
-    const int pl = P.n_set - __builtin_popcount(H);
-    return (pl < 0 || pl > P.k) ? 0ull : binom_u64(P.k, pl);
-  };
-  // prefix[h] = rows of the tiles h' < h in the lower half, and the same for the upper half
-  std::vector<uint64_t> pre_lo(top + 1, 0), pre_hi(top + 1, 0);
-  for (uint32_t h = 0; h < top; ++h) {
-    pre_lo[h + 1] = pre_lo[h] + tile_rows(h);
-    pre_hi[h + 1] = pre_hi[h] + tile_rows(h | top);
-  }
-  const uint64_t total = pre_lo[top] + pre_hi[top];
-  auto cut = [&](int r) -> uint32_t {   // first h whose combined prefix reaches r/world of all rows
-    if (r <= 0) return 0;
-    if (r >= world) return top;
-    const uint64_t target = total / (uint64_t)world * (uint64_t)r;
-    uint32_t a = 0, b = top;
-    while (a < b) { const uint32_t m = (a + b) / 2; if (pre_lo[m] + pre_hi[m] < target) a = m + 1; else b = m; }
-    return a;
-  };
-  const uint32_t h0 = cut(rank), h1 = cut(rank + 1);
-  lo[0] = (int64_t)pre_lo[h0]; hi[0] = (int64_t)pre_lo[h1];
-  lo[1] = (int64_t)(pre_lo[top] + pre_hi[h0]); hi[1] = (int64_t)(pre_lo[top] + pre_hi[h1]);
-  return 2;
+  order.resize(nt);
+  for (size_t t = 0; t < nt; ++t) order[t] = (uint32_t)t;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key[x] < key[y]; });
 }
 
-// Rows of x outside the given local ranges that the fast kernel reads for the tiles inside them: whole neighbour tiles,
-// merged into ascending disjoint ranges (what the copy engines must bring into the mirror vector before the remote pass).
-void ed_u1_remote_rows(ed_oprep* o, int dtype, int n_ranges, const int64_t* lo, const int64_t* hi, std::vector<int64_t>& out_lo,
-                       std::vector<int64_t>& out_hi) {
-  FastU1Plan* plan = get_plan(o, dtype);
-  ED_REQUIRE(plan->supported, ED_ERR_UNSUPPORTED, "remote rows are defined for the U(1) fast-path kernel only");
+std::shared_ptr<U1Global> u1_global_layout(const FastU1Plan* plan, int world, int n_chunks, int policy) {
+  auto Gp = std::make_shared<U1Global>();
+  U1Global& G = *Gp;
+  const size_t nt = plan->h_tile_H.size();
   const int hb = plan->hb;
-  const U1Params& P = plan->P;
-  // host copies of the bond lists
-  std::vector<uint8_t> hh_p(std::max(P.n_hh, 1)), hh_q(std::max(P.n_hh, 1)), mx_q(std::max(P.n_mx, 1)), ms_q(std::max(P.n_ms, 1));
-  plan->hh_p.download(hh_p.data(), hh_p.size()); plan->hh_q.download(hh_q.data(), hh_q.size());
-  plan->mx_q.download(mx_q.data(), mx_q.size()); plan->ms_q.download(ms_q.data(), ms_q.size());
-  const size_t nt = plan->h_base.size();
-  std::vector<uint32_t> tile_H(nt);
-  plan->tile_H.download(tile_H.data(), nt);
-  std::vector<int32_t> index_of((size_t)1 << hb, -1);
-  for (size_t t = 0; t < nt; ++t) index_of[tile_H[t]] = (int32_t)t;
-  auto is_local = [&](size_t t) {
-    const int64_t b = (int64_t)plan->h_base[t];
-    for (int r = 0; r < n_ranges; ++r) if (b >= lo[r] && b < hi[r]) return true;
-    return false;
-  };
-  std::vector<uint8_t> need(nt, 0);
-  for (size_t t = 0; t < nt; ++t) {
-    if (!is_local(t)) continue;
-    const uint32_t H = tile_H[t];
-    auto touch = [&](uint32_t H2) { const int32_t j = index_of[H2]; if (j >= 0 && !is_local((size_t)j)) need[j] = 1; };
-    for (int b = 0; b < P.n_hh; ++b)
-      if (((H >> hh_p[b]) ^ (H >> hh_q[b])) & 1u) touch(H ^ ((1u << hh_p[b]) | (1u << hh_q[b])));
-    for (int b = 0; b < P.n_mx; ++b) touch(H ^ (1u << mx_q[b]));
-    for (int b = 0; b < P.n_ms; ++b) touch(H ^ (1u << ms_q[b]));
+  const TileGraph TG = u1_tile_graph(plan);
+  G.world = world;
+  // ---- choose the ordering
+  std::vector<KeySpec> cands;
+  const bool wrap_ok = plan->wraps && hb >= 2 && (1 << (hb - 1)) >= 4 * world;
+  if (policy == 0 || policy == 1) cands.push_back({"ascending ranges", 0, 0, -1, 0});
+  if ((policy == 0 || policy == 2) && wrap_ok) cands.push_back({"wrap-aware ranges", 1, 0, -1, 0});
+  if (policy == 2 && !wrap_ok) cands.push_back({"ascending ranges", 0, 0, -1, 0});
+  if ((policy == 0 || policy == 3) && world > 1 && hb >= 4) {
+    for (int a0 = 0; a0 <= std::min(2, hb - 3); ++a0)
+      for (int b1 = std::max(a0 + 3, hb - 2); b1 <= hb; ++b1) {
+        cands.push_back({"popcount[" + std::to_string(a0) + "," + std::to_string(b1) + ")", 2, a0, -1, b1});
+        for (int s = a0 + 2; s <= b1 - 2; ++s)
+          cands.push_back({"popcount[" + std::to_string(a0) + "," + std::to_string(s) + ")[" + std::to_string(s) + "," + std::to_string(b1) + ")", 2, a0, s, b1});
+      }
   }
-  out_lo.clear(); out_hi.clear();
-  for (size_t t = 0; t < nt; ++t) {
-    if (!need[t]) continue;
-    const int64_t b = (int64_t)plan->h_base[t], e = b + (int64_t)plan->h_size[t];
-    if (!out_hi.empty() && out_hi.back() == b) out_hi.back() = e;
-    else { out_lo.push_back(b); out_hi.push_back(e); }
+  if (cands.empty()) cands.push_back({"ascending ranges", 0, 0, -1, 0});
+  std::vector<uint32_t> order, best_order;
+  std::vector<int> owner;
+  uint64_t best = ~0ull;
+  for (const KeySpec& K : cands) {
+    u1_order_by_key(plan, K, order);
+    u1_cut(plan, order, world, owner);
+    const uint64_t h = world > 1 ? u1_max_halo(plan, TG, owner, world) : 0;
+    if (h < best) { best = h; best_order = order; G.owner = owner; G.key_name = K.name; }
+    if (world == 1) break;
   }
+  // ---- storage: every rank keeps its tiles in ascending H (fewest global row ranges); launch order = the key's order
+  G.rows_of_rank.assign(world, 0);
+  G.off.assign(nt, 0);
+  for (size_t t = 0; t < nt; ++t) { G.off[t] = G.rows_of_rank[G.owner[t]]; G.rows_of_rank[G.owner[t]] += (int64_t)plan->h_size[t]; }
+  G.launch.assign(world, {});
+  for (uint32_t t : best_order) G.launch[G.owner[t]].push_back(t);
+  size_t most = 1;
+  for (auto& l : G.launch) most = std::max(most, l.size());
+  n_chunks = world > 1 ? (int)std::max<size_t>(1, std::min<size_t>((size_t)n_chunks, most)) : 1;
+  G.n_chunks = n_chunks;
+  G.chunk_first.assign(world, std::vector<int>(n_chunks + 1, 0));
+  G.halo_tiles.assign(world, {});
+  G.halo_chunk.assign(world, {});
+  G.exch.assign((size_t)world * world * n_chunks, 0);
+  for (int r = 0; r < world; ++r) {
+    const auto& L = G.launch[r];
+    auto& cf = G.chunk_first[r];
+    for (int c = 0; c <= n_chunks; ++c) cf[c] = (int)L.size();
+    cf[0] = 0;
+    int c = 1;
+    int64_t acc = 0;
+    for (size_t i = 0; i < L.size() && c < n_chunks; ++i) {
+      acc += (int64_t)plan->h_size[L[i]];
+      if (acc >= G.rows_of_rank[r] / n_chunks * c) cf[c++] = (int)i + 1;
+    }
+    std::vector<uint8_t> seen(nt, 0);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      std::vector<uint32_t> fresh;
+      for (int i = cf[ch]; i < cf[ch + 1]; ++i) {
+        const int32_t* row = TG.nbr.data() + (size_t)L[i] * TG.deg;
+        for (int d = 0; d < TG.deg; ++d) {
+          const int32_t j = row[d];
+          if (j >= 0 && G.owner[j] != r && !seen[j]) { seen[j] = 1; fresh.push_back((uint32_t)j); }
+        }
+      }
+      std::sort(fresh.begin(), fresh.end(), [&](uint32_t x, uint32_t y) { return G.owner[x] != G.owner[y] ? G.owner[x] < G.owner[y] : x < y; });
+      for (uint32_t t : fresh) {
+        G.halo_tiles[r].push_back(t);
+        G.halo_chunk[r].push_back(ch);
+        G.exch[((size_t)G.owner[t] * world + r) * n_chunks + ch] += (int64_t)plan->h_size[t];
+      }
+    }
+  }
+  return Gp;
 }
 
-void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
-  (void)side;
-  FastU1Plan* plan = get_plan(o, dtype);
-  ED_REQUIRE(plan->supported, ED_ERR_INTERNAL, "u1 fast path requested for an unsupported representation");
-  U1Params P = plan->P;
-  P.row_lo = o->row_lo;
-  P.row_hi = o->row_hi;
-  P.accumulate = accumulate;
-  // profiling knob (results are WRONG when set): drop parts of the kernel to measure what each costs
+}  // namespace
+
+// Everything rank `rank` needs to run its share of the tiled matvec: its tiles (launch order), their offsets in the local
+// vectors (ascending-H storage), the directory that resolves any tile it reads to "local vector + offset" or "halo
+// buffer + offset", what it PACKS for its peers (the tiles they read, gathered into one send buffer, receiver-major then
+// by the receiver's launch chunk) and what it PULLS (one contiguous piece per peer and chunk).  The chunks are launched
+// in order, each waiting only for its own pieces: the transfer of chunk c+1 overlaps the kernel of chunk c.
+void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunks, int policy, U1ShardLayout* out) {
+  ED_REQUIRE(plan && plan->supported, ED_ERR_UNSUPPORTED, "the shard layout is defined for the tiled U(1) kernel only");
+  ED_REQUIRE(world >= 1 && rank >= 0 && rank < world && n_chunks >= 1, ED_ERR_ARGUMENT, "bad rank / world / chunks");
+  // the global layout is the same for every rank: cached per (plan, world, chunks, policy) so that a process driving
+  // several GPUs computes it once
+  static thread_local struct { const FastU1Plan* plan = nullptr; int world = 0, chunks = 0, policy = 0; size_t nt = 0; std::shared_ptr<U1Global> G; } cache;
+  if (!(cache.G && cache.plan == plan && cache.world == world && cache.chunks == n_chunks && cache.policy == policy && cache.nt == plan->h_tile_H.size())) {
+    cache.G = u1_global_layout(plan, world, n_chunks, policy);
+    cache.plan = plan; cache.world = world; cache.chunks = n_chunks; cache.policy = policy; cache.nt = plan->h_tile_H.size();
+  }
+  const U1Global& G = *cache.G;
+  const size_t nt = plan->h_tile_H.size();
+  const int hb = plan->hb;
+  U1ShardLayout& S = *out;
+  S = U1ShardLayout();
+  S.world = world; S.rank = rank; S.n_chunks = G.n_chunks;
+  S.key_name = G.key_name;
+  S.rows_of_rank = G.rows_of_rank;
+  S.n_local = G.rows_of_rank[rank];
+  S.dir.assign((size_t)1 << hb, -1);
+  for (size_t t = 0; t < nt; ++t)
+    if (G.owner[t] == rank) {
+      S.dir[plan->h_tile_H[t]] = G.off[t];
+      const int64_t b = (int64_t)plan->h_base[t], e = b + (int64_t)plan->h_size[t];
+      if (!S.range_hi.empty() && S.range_hi.back() == b) S.range_hi.back() = e;
+      else { S.range_lo.push_back(b); S.range_hi.push_back(e); }
+    }
+  for (uint32_t t : G.launch[rank]) { S.tile_H.push_back(plan->h_tile_H[t]); S.tile_off.push_back(G.off[t]); }
+  S.chunk_first = G.chunk_first[rank];
+  // halo + pulls
+  int64_t halo = 0;
+  const auto& ht = G.halo_tiles[rank];
+  const auto& hc = G.halo_chunk[rank];
+  for (size_t i = 0; i < ht.size(); ++i) {
+    const uint32_t t = ht[i];
+    const int p = G.owner[t];
+    const int64_t len = (int64_t)plan->h_size[t];
+    S.dir[plan->h_tile_H[t]] = halo | U1_DIR_HALO;
+    if (!S.pulls.empty() && S.pulls.back().peer == p && S.pulls.back().chunk == hc[i]) S.pulls.back().len += len;
+    else S.pulls.push_back({p, hc[i], G.send_off(p, rank, hc[i]), halo, len});
+    halo += len;
+  }
+  S.n_halo = halo;
+  // packs: for every receiver (ascending) and chunk, its halo tiles owned by this rank, in its halo order
+  int64_t send = 0;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    const auto& rt = G.halo_tiles[r];
+    for (size_t i = 0; i < rt.size(); ++i) {
+      const uint32_t t = rt[i];
+      if (G.owner[t] != rank) continue;
+      const int64_t len = (int64_t)plan->h_size[t];
+      if (!S.packs.empty() && S.packs.back().src_off + S.packs.back().len == G.off[t] && S.packs.back().dst_off + S.packs.back().len == send)
+        S.packs.back().len += len;
+      else S.packs.push_back({G.off[t], send, len});
+      send += len;
+    }
+  }
+  S.n_send = send;
+}
+
+// Launch order of whole-basis launches (EDCUDA_U1_ORDER): "class" = tiles grouped by popcount(H) -- the tiles running at
+// the same time then share one ELL table and their high-bit neighbours (same popcount) are 4-5x closer in launch order, so
+// more of the far bonds hit the L2 -- or "key:a,s,b" = the shard planner's popcount-block ordering [a,s)[s,b) (s = -1:
+// one block).  Unset: ascending H.
+static void u1_apply_env_order(FastU1Plan* plan) {
+  const char* e = getenv("EDCUDA_U1_ORDER");
+  if (!e || !*e) return;
+  std::vector<uint32_t> order;
+  int a = 0, sp = -1, b = 0;
+  if (!strcmp(e, "class")) u1_order_by_key(plan, {"class", 2, 0, -1, plan->hb}, order);
+  else if (sscanf(e, "key:%d,%d,%d", &a, &sp, &b) == 3 && a >= 0 && b <= plan->hb && a < b) u1_order_by_key(plan, {"key", 2, a, sp, b}, order);
+  else return;
+  plan->tile_order.upload(order);
+  ED_CUDA(cudaStreamSynchronize(ed_stream()));
+  plan->order_on = true;
+}
+
+static void u1_fill_params(ed_oprep* o, U1Params& P) {
+  // profiling knobs, compiled in only with -DEDCUDA_PROFILING (EDCUDA_U1_ABLATE drops parts of the Hamiltonian: results are WRONG)
+#ifdef EDCUDA_PROFILING
   static const int ablate = getenv("EDCUDA_U1_ABLATE") ? atoi(getenv("EDCUDA_U1_ABLATE")) : 0;
   static const int far_bit = getenv("EDCUDA_U1_FARBIT") ? atoi(getenv("EDCUDA_U1_FARBIT")) : -1;   // override of the plan's choice
   if (far_bit >= 0) P.far_bit = far_bit;
-  P.stream_mode = o->x_seg_ptr.empty() ? 0 : o->exchange_mode;
-  P.local_seg_mask = o->local_seg_mask;
-  P.mirror = o->mirror;
-  if (P.stream_mode == 2) {                 // remote pass: neighbour streams only, added to what the local pass wrote
-    ED_REQUIRE(o->mirror != nullptr, ED_ERR_ARGUMENT, "remote pass without a mirror vector (ed_oprep_set_exchange)");
-    P.n_ll = 0;
-    P.accumulate = 1;
-  }
   if (ablate & 1) P.n_ll = 0;
   if (ablate & 2) P.n_hh = 0;
   if (ablate & 4) P.n_mx = 0;
   if (ablate & 8) P.n_ms = 0;
   if (ablate & 16) P.n_mq = 0;
   if (ablate & 32) P.diag_mode = 0;
-  if (o->x_seg_ptr.empty()) {
-    ED_REQUIRE(x != nullptr, ED_ERR_ARGUMENT, "null input vector");
-    P.n_seg = 1;
-    P.seg_lo[0] = 0; P.seg_lo[1] = o->dim;
-    P.seg_ptr[0] = x;
-  } else {
-    P.n_seg = (int)o->x_seg_ptr.size();
-    for (int s = 0; s <= P.n_seg; ++s) P.seg_lo[s] = o->x_seg_lo[s];
-    for (int s = 0; s < P.n_seg; ++s) {
-      P.seg_ptr[s] = o->x_seg_ptr[s];
-      if (s > 0) {
-        const uint64_t b = (uint64_t)o->x_seg_lo[s];
-        ED_REQUIRE(b == (uint64_t)o->dim || std::binary_search(plan->h_base.begin(), plan->h_base.end(), b), ED_ERR_ARGUMENT,
-                   "x segment boundaries must fall on tile boundaries (use ed_oprep_suggest_rows)");
-      }
-    }
-  }
+#endif
+  (void)o;
+}
+
+void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
+  (void)side;
+  FastU1Plan* plan = get_plan(o, dtype);
+  ED_REQUIRE(plan->supported, ED_ERR_INTERNAL, "u1 fast path requested for an unsupported representation");
+  ED_REQUIRE(x != nullptr, ED_ERR_ARGUMENT, "null input vector");
+  U1Params P = plan->P;
+  P.row_lo = o->row_lo;
+  P.row_hi = o->row_hi;
+  P.accumulate = accumulate;
+  P.stream_mode = 0;
+  P.dir = nullptr;
+  P.x_local = x;
+  P.x_halo = nullptr;
+  P.partial_first = 0;
+  u1_fill_params(o, P);
   // tiles overlapping the owned rows [row_lo, row_hi)
   int first = (int)(std::upper_bound(plan->h_base.begin(), plan->h_base.end(), (uint64_t)std::max<int64_t>(o->row_lo, 0)) - plan->h_base.begin()) - 1;
   first = std::max(first, 0);
@@ -1170,4 +1371,83 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   if (dtype == ED_F64) launch_u1<double, 7>(plan, P, n_launch, out, partials);
   else launch_u1<c128, 7>(plan, P, n_launch, out, partials);
   if (alpha_dot) ed_reduce_pairs(partials, n_launch, alpha_dot);
+}
+
+// One chunk of a rank's tiles (sharded matvec, ctx.cu): x through the directory, y and the dot partials by tile slot.
+void ed_apply_u1_sharded(ed_oprep* o, int dtype, const U1ShardLaunch& L) {
+  FastU1Plan* plan = get_plan(o, dtype);
+  ED_REQUIRE(plan->supported, ED_ERR_INTERNAL, "u1 fast path requested for an unsupported representation");
+  if (L.count <= 0) return;
+  U1Params P = plan->P;
+  P.row_lo = 0;
+  P.row_hi = INT64_MAX;
+  P.accumulate = L.stream_mode == 2 ? 1 : L.accumulate;
+  P.stream_mode = L.stream_mode;
+  if (P.stream_mode == 2) P.n_ll = 0;      // remote pass: neighbour streams only, added to what the local pass wrote
+  P.dir = L.dir;
+  P.x_local = L.x_local;
+  P.x_halo = L.x_halo;
+  P.tile_H = L.tile_H;
+  P.tile_first = L.first;
+  P.partial_first = L.first;
+  P.tile_order = nullptr;
+  u1_fill_params(o, P);
+  if (dtype == ED_F64) launch_u1<double, 7>(plan, P, L.count, L.y_local, L.partials);
+  else launch_u1<c128, 7>(plan, P, L.count, L.y_local, L.partials);
+}
+
+// Host-only description of the shard layout (no device needed): what tests/test_shard_plan.py replays on CPU with gloo.
+extern "C" int ed_shard_plan_describe(const ed_operator* op, int32_t n_bits, int32_t n_set, int32_t dtype, int32_t world, int32_t rank,
+                                      int32_t n_chunks, int32_t policy, int64_t* counts, int64_t* ranges, int64_t* tiles,
+                                      int64_t* pulls, int64_t* packs, int64_t* reads) {
+  ED_TRY
+  ED_REQUIRE(op && counts, ED_ERR_ARGUMENT, "null argument");
+  ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
+  std::shared_ptr<FastU1Plan> plan = ed_u1_host_plan(*op, n_bits, n_set, dtype);
+  ED_REQUIRE(plan->supported, ED_ERR_UNSUPPORTED, "the operator does not lower to the tiled U(1) kernel");
+  U1ShardLayout S;
+  ed_u1_shard_layout(plan.get(), world, rank, n_chunks, policy, &S);
+  std::vector<int32_t> index_of((size_t)1 << plan->hb, -1);
+  for (size_t t = 0; t < plan->h_tile_H.size(); ++t) index_of[plan->h_tile_H[t]] = (int32_t)t;
+  int64_t n_reads = 0;
+  auto each_read = [&](auto&& f) {
+    for (size_t i = 0; i < S.tile_H.size(); ++i) {
+      const uint32_t H = S.tile_H[i];
+      auto touch = [&](uint32_t H2) { if (index_of[H2] >= 0) f((int64_t)i, index_of[H2], H2); };
+      for (int b = 0; b < plan->n_hh; ++b)
+        if (((H >> plan->h_hh_p[b]) ^ (H >> plan->h_hh_q[b])) & 1u) touch(H ^ ((1u << plan->h_hh_p[b]) | (1u << plan->h_hh_q[b])));
+      for (int b = 0; b < plan->n_mx; ++b) touch(H ^ (1u << plan->h_mx_q[b]));
+      for (int b = 0; b < plan->n_ms; ++b) touch(H ^ (1u << plan->h_ms_q[b]));
+    }
+  };
+  each_read([&](int64_t, int32_t, uint32_t) { ++n_reads; });
+  uint64_t dim = 0;
+  for (uint64_t v : plan->h_size) dim += v;
+  counts[0] = S.n_local; counts[1] = S.n_halo; counts[2] = (int64_t)S.range_lo.size(); counts[3] = (int64_t)S.tile_H.size();
+  counts[4] = (int64_t)S.pulls.size(); counts[5] = n_reads; counts[6] = S.n_chunks; counts[7] = (int64_t)dim;
+  counts[8] = (int64_t)S.packs.size(); counts[9] = S.n_send;
+  if (packs)
+    for (size_t i = 0; i < S.packs.size(); ++i) { packs[3 * i] = S.packs[i].src_off; packs[3 * i + 1] = S.packs[i].dst_off; packs[3 * i + 2] = S.packs[i].len; }
+  if (ranges) for (size_t k = 0; k < S.range_lo.size(); ++k) { ranges[2 * k] = S.range_lo[k]; ranges[2 * k + 1] = S.range_hi[k]; }
+  if (tiles)
+    for (size_t i = 0; i < S.tile_H.size(); ++i) {
+      const int32_t t = index_of[S.tile_H[i]];
+      tiles[4 * i] = (int64_t)plan->h_base[t]; tiles[4 * i + 1] = (int64_t)plan->h_size[t]; tiles[4 * i + 2] = S.tile_off[i];
+      int c = 0;
+      while (c + 1 < S.n_chunks && (int)i >= S.chunk_first[c + 1]) ++c;
+      tiles[4 * i + 3] = c;
+    }
+  if (pulls)
+    for (size_t i = 0; i < S.pulls.size(); ++i) {
+      pulls[5 * i] = S.pulls[i].peer; pulls[5 * i + 1] = S.pulls[i].chunk; pulls[5 * i + 2] = S.pulls[i].src_off;
+      pulls[5 * i + 3] = S.pulls[i].dst_off; pulls[5 * i + 4] = S.pulls[i].len;
+    }
+  if (reads) {
+    int64_t k = 0;
+    each_read([&](int64_t i, int32_t t2, uint32_t H2) {
+      reads[4 * k] = i; reads[4 * k + 1] = (int64_t)plan->h_base[t2]; reads[4 * k + 2] = (int64_t)plan->h_size[t2]; reads[4 * k + 3] = S.dir[H2];
+      ++k;
+    });
+  }
+  ED_CATCH
 }

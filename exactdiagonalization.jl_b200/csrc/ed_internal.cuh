@@ -66,6 +66,8 @@ int ed_sm_count();
     ED_CUDA(cudaGetLastError());                                          \
   } while (0)
 
+int ed_current_device();            // runtime.cu
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -101,6 +103,14 @@ struct DevBuf {
     }
   }
 };
+
+// Scratch buffers that persist between calls are kept per host thread AND per device (one process may drive several
+// GPUs through an ed_ctx): TAG distinguishes the call sites.
+template <typename T, int TAG>
+DevBuf<T>& ed_scratch() {
+  static thread_local DevBuf<T> buf[16];
+  return buf[ed_current_device() & 15];
+}
 
 // Stages a caller buffer (host or device) as a device pointer for the duration of a call.
 struct Staged {
@@ -210,8 +220,6 @@ struct SymDev {
   int n_chunks = 0;        // ceil(bits / 8)
   uint64_t fullmask = 0;
   DevBuf<uint64_t> lut;    // [(g*n_chunks + c)*256 + byte] -> image bits (flip already folded in chunk 0.. see symmetry.cu)
-  DevBuf<uint8_t> tgt_bit;   // [g][64] target position of every bit (reduced_linear.cu)
-  DevBuf<uint64_t> flipmask; // [g] fullmask when the element carries a GlobalBitFlip, else 0
   int n_chunks6 = 0;       // ceil(bits / 6)
   DevBuf<uint64_t> lut6;   // [(g*n_chunks6 + c)*64 + v]: the same action in 6-bit chunks (shared-memory streaming, reduced_staged.cu)
   DevBuf<double> chi;      // [n_ops][2]
@@ -288,12 +296,6 @@ struct ed_oprep {
   int64_t dim = 0;
   int64_t row_lo = 0, row_hi = 0;
   int kernel_choice = 0;
-  // x handed over as contiguous segments (multi-GPU: peers' shards mapped over NVLink); empty = plain pointer
-  int exchange_mode = 0;            // 0 one pass through the segments, 1 local pass, 2 remote pass from the mirror
-  uint32_t local_seg_mask = 0;
-  const void* mirror = nullptr;
-  std::vector<int64_t> x_seg_lo;
-  std::vector<const void*> x_seg_ptr;
   TermsDev terms_left, terms_right;
   bool terms_ready = false;
   std::shared_ptr<FastU1Plan> u1plan, u1plan_c;  // f64 / c128 vectors
@@ -314,13 +316,42 @@ bool ed_apply_u1_supported(ed_oprep* o, int dtype, int side);                   
 void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate,
                  double* alpha_dot);
 void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);
-void ed_u1_remote_rows(ed_oprep* o, int dtype, int n_ranges, const int64_t* lo, const int64_t* hi, std::vector<int64_t>& out_lo,
-                       std::vector<int64_t>& out_hi);                                             // apply_u1.cu
-int ed_u1_suggest_rows2(ed_oprep* o, int dtype, int world, int rank, int64_t* lo, int64_t* hi);   // apply_u1.cu
+// ---- sharded tiled matvec (apply_u1.cu; driven by ctx.cu) -----------------------------------------------------------
+struct U1Pull { int peer; int chunk; int64_t src_off, dst_off, len; };   // elements: peer's SEND buffer -> this rank's halo
+struct U1Pack { int64_t src_off, dst_off, len; };                        // elements: this rank's x -> its send buffer
+struct U1ShardLayout {
+  int world = 1, rank = 0, n_chunks = 1;
+  int64_t n_local = 0, n_halo = 0, n_send = 0; // elements
+  std::string key_name;                        // the tile ordering the planner chose
+  std::vector<int64_t> range_lo, range_hi;     // global row ranges owned by this rank, ascending; local order = this order
+  std::vector<uint32_t> tile_H;                // this rank's tiles in launch order
+  std::vector<int64_t> tile_off;               // their offsets in the local vectors (storage is ascending in H)
+  std::vector<U1Pack> packs;                   // what this rank gathers into its send buffer for its peers
+  std::vector<int> chunk_first;                // [n_chunks + 1] positions in tile_H
+  std::vector<int64_t> dir;                    // [2^hb] see U1Params::dir
+  std::vector<U1Pull> pulls;                   // ordered by chunk, one per (chunk, peer)
+  std::vector<int64_t> rows_of_rank;           // [world]
+};
+struct U1ShardLaunch {
+  const uint32_t* tile_H;      // device copy of U1ShardLayout::tile_H
+  int first, count;            // the chunk launched by this call
+  const int64_t* dir;          // device copy of U1ShardLayout::dir
+  const void* x_local;
+  const void* x_halo;
+  void* y_local;
+  int stream_mode, accumulate;
+  double* partials;            // device, 2 doubles per tile of this rank, or nullptr
+};
+FastU1Plan* ed_u1_plan(ed_oprep* o, int dtype);                                                  // nullptr: not supported
+std::shared_ptr<FastU1Plan> ed_u1_host_plan(const ed_operator& op, int n_bits, int n_set, int dtype);   // no device needed
+void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunks, int policy, U1ShardLayout* out);
+void ed_apply_u1_sharded(ed_oprep* o, int dtype, const U1ShardLaunch& L);
+void ed_reduce_pairs(const double* partials, int n, double* out2);                              // apply.cu
+int ed_lanczos_finish(const double* hd, const double* hn, int n_steps, double* alpha, double* beta, double* ritz, int n_ritz);   // lanczos.cu
+void ed_push_stream(cudaStream_t s);    // runtime.cu: run this thread's library work on s until ed_pop_stream()
+void ed_pop_stream();
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,
                       double* alpha_dot);
-bool ed_apply_reduced_linear_supported(ed_oprep* o);                                            // reduced_linear.cu
-void ed_apply_reduced_linear(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);
 bool ed_reduced_fill_raw_staged(ed_oprep* o, int side, int64_t line0, int64_t n, const int64_t* raw_offs, int64_t* raw_row, void* raw_val);  // reduced_staged.cu
 bool ed_apply_reduced_staged_supported(ed_oprep* o);                                            // reduced_staged.cu
 void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot);                                                       // reduced.cu (K6)

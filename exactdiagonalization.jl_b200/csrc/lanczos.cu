@@ -157,7 +157,7 @@ static int grid_rows(int64_t n) {
 }
 
 static DevBuf<double>& partial_scratch(int n_blocks) {
-  static thread_local DevBuf<double> buf;
+  DevBuf<double>& buf = ed_scratch<double, 2>();
   if (buf.n < (size_t)2 * n_blocks) buf.alloc((size_t)2 * n_blocks);
   return buf;
 }
@@ -230,7 +230,50 @@ static void tridiag_eig(std::vector<double> d, std::vector<double> e, std::vecto
   out = d;
 }
 
+// (alpha, beta, Ritz values) from the device-resident scalars d_j = <u_j, H u_j> and |u_j|^2 (interleaved pairs as the
+// kernels write them).  Stops at an invariant subspace: beta_j below roundoff of the tridiagonal's scale -- a running
+// estimate of ||T|| = max(|alpha| + beta) times 1e-10 -- means the next Krylov vector is noise divided by its own norm,
+// and every later Ritz value would be a ghost.  Returns the number of valid (alpha, beta) pairs.
+int ed_lanczos_finish(const double* hd, const double* hn, int n_steps, double* alpha, double* beta, double* ritz, int n_ritz) {
+  int done = 0;
+  double t_norm = 0.0;
+  for (int j = 0; j < n_steps; ++j) {
+    if (!(hn[2 * j] > 0.0) || !std::isfinite(hn[2 * j])) break;
+    alpha[j] = hd[2 * j] / hn[2 * j];
+    beta[j] = std::sqrt(hn[2 * (j + 1)]);
+    if (!std::isfinite(alpha[j]) || !std::isfinite(beta[j])) break;
+    ++done;
+    t_norm = std::max(t_norm, std::fabs(alpha[j]) + beta[j]);
+    if (!(beta[j] > 1e-10 * t_norm + 1e-300)) break;
+  }
+  if (ritz && n_ritz > 0) {
+    for (int i = 0; i < n_ritz; ++i) ritz[i] = NAN;
+    if (done > 0) {
+      std::vector<double> d(alpha, alpha + done), e(done, 0.0), out;
+      for (int i = 0; i + 1 < done; ++i) e[i] = beta[i];
+      tridiag_eig(d, e, out);
+      for (int i = 0; i < n_ritz && i < done; ++i) ritz[i] = out[i];
+    }
+  }
+  return done;
+}
+
+__global__ void __launch_bounds__(256) k_scale(double* __restrict__ v, int64_t n, double a) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] *= a;
+}
+
 extern "C" {
+
+int ed_vector_scale_async(void* v, int64_t n, int32_t dtype, double a) {
+  ED_TRY
+  ED_REQUIRE(v || n == 0, ED_ERR_ARGUMENT, "null vector");
+  ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
+  if (n == 0) return ED_OK;
+  ed_require_device();
+  const int64_t nd = dtype == ED_C128 ? 2 * n : n;
+  ED_LAUNCH(k_scale, grid_rows(nd), 256, 0, reinterpret_cast<double*>(v), nd, a);
+  ED_CATCH
+}
 
 int ed_tridiag_eigvals(const double* alpha, const double* beta, int32_t k, double* eig_out) {
   ED_TRY
@@ -310,22 +353,8 @@ int ed_lanczos(ed_oprep* oprep, int32_t n_steps, const void* v0, int32_t dtype, 
   std::vector<double> hd((size_t)2 * n_steps), hn((size_t)2 * (n_steps + 1));
   dots.download(hd.data(), hd.size());
   norms.download(hn.data(), hn.size());
-  int done = 0;
-  for (int j = 0; j < n_steps; ++j) {
-    if (!(hn[2 * j] > 0.0) || !std::isfinite(hn[2 * j])) break;
-    alpha[j] = hd[2 * j] / hn[2 * j];
-    beta[j] = std::sqrt(hn[2 * (j + 1)]);
-    ++done;
-    // invariant subspace reached: later vectors are numerical noise
-    if (!(beta[j] > 1e-13 * std::fabs(alpha[j]) + 1e-300)) break;
-  }
+  const int done = ed_lanczos_finish(hd.data(), hn.data(), n_steps, alpha, beta, ritz, n_ritz);
   if (steps_done) *steps_done = done;
-  if (ritz && n_ritz > 0 && done > 0) {
-    std::vector<double> d(alpha, alpha + done), e(done, 0.0), out;
-    for (int i = 0; i + 1 < done; ++i) e[i] = beta[i];
-    tridiag_eig(d, e, out);
-    for (int i = 0; i < n_ritz; ++i) ritz[i] = i < done ? out[i] : NAN;
-  }
   ED_CATCH
 }
 

@@ -174,66 +174,6 @@ int ed_oprep_suggest_rows(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t
   ED_CATCH
 }
 
-int ed_oprep_suggest_row_ranges(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi,
-                                int32_t* n_ranges) {
-  ED_TRY
-  ED_REQUIRE(oprep && row_lo && row_hi && n_ranges, ED_ERR_ARGUMENT, "null argument");
-  ED_REQUIRE(world >= 1 && rank >= 0 && rank < world, ED_ERR_ARGUMENT, "bad rank / world");
-  if (!oprep->rbasis && oprep->kernel_choice == 0 && ed_device_count() > 0 && ed_apply_u1_supported(oprep, dtype, ED_SIDE_LEFT)) {
-    *n_ranges = ed_u1_suggest_rows2(oprep, dtype, world, rank, row_lo, row_hi);
-  } else {
-    const int rc = ed_oprep_suggest_rows(oprep, dtype, world, rank, row_lo, row_hi);
-    ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
-    *n_ranges = 1;
-  }
-  if (*n_ranges == 1) { row_lo[1] = row_hi[0]; row_hi[1] = row_hi[0]; }
-  ED_CATCH
-}
-
-int ed_oprep_remote_rows(ed_oprep* oprep, int32_t dtype, int32_t n_ranges, const int64_t* row_lo, const int64_t* row_hi,
-                         int32_t capacity, int64_t* out_lo, int64_t* out_hi, int32_t* n_out) {
-  ED_TRY
-  ED_REQUIRE(oprep && row_lo && row_hi && n_out && n_ranges >= 1, ED_ERR_ARGUMENT, "bad argument");
-  ED_REQUIRE(!oprep->rbasis && ed_apply_u1_supported(oprep, dtype, ED_SIDE_LEFT), ED_ERR_UNSUPPORTED,
-             "remote rows are defined for the U(1) fast-path kernel only");
-  std::vector<int64_t> lo, hi;
-  ed_u1_remote_rows(oprep, dtype, n_ranges, row_lo, row_hi, lo, hi);
-  *n_out = (int32_t)lo.size();
-  if (out_lo && out_hi) {
-    ED_REQUIRE(capacity >= (int32_t)lo.size(), ED_ERR_ARGUMENT, "output capacity too small (call with NULL outputs to query the count)");
-    for (size_t i = 0; i < lo.size(); ++i) { out_lo[i] = lo[i]; out_hi[i] = hi[i]; }
-  }
-  ED_CATCH
-}
-
-int ed_oprep_set_exchange(ed_oprep* oprep, int32_t mode, const void* mirror, uint32_t local_segment_mask) {
-  ED_TRY
-  ED_REQUIRE(oprep && mode >= 0 && mode <= 2, ED_ERR_ARGUMENT, "bad argument");
-  ED_REQUIRE(mode != 2 || mirror, ED_ERR_ARGUMENT, "the remote pass needs a mirror vector");
-  oprep->exchange_mode = mode;
-  oprep->mirror = mirror;
-  oprep->local_seg_mask = local_segment_mask;
-  ED_CATCH
-}
-
-int ed_oprep_set_x_segments(ed_oprep* oprep, int32_t n_seg, const int64_t* seg_lo, const void* const* seg_ptr) {
-  ED_TRY
-  ED_REQUIRE(oprep, ED_ERR_ARGUMENT, "null argument");
-  ED_REQUIRE(n_seg >= 0 && n_seg <= 16, ED_ERR_ARGUMENT, "n_seg must be in 0..16");
-  oprep->x_seg_lo.clear();
-  oprep->x_seg_ptr.clear();
-  if (n_seg == 0) return ED_OK;
-  ED_REQUIRE(seg_lo && seg_ptr, ED_ERR_ARGUMENT, "null argument");
-  ED_REQUIRE(seg_lo[0] == 0 && seg_lo[n_seg] == oprep->dim, ED_ERR_DIMENSION_MISMATCH, "segments must cover rows 0..dim");
-  for (int s = 0; s < n_seg; ++s) {
-    ED_REQUIRE(seg_lo[s] <= seg_lo[s + 1], ED_ERR_ARGUMENT, "segment boundaries must be ascending");
-    ED_REQUIRE(seg_ptr[s] != nullptr || seg_lo[s] == seg_lo[s + 1], ED_ERR_ARGUMENT, "null segment pointer");
-  }
-  oprep->x_seg_lo.assign(seg_lo, seg_lo + n_seg + 1);
-  oprep->x_seg_ptr.assign(seg_ptr, seg_ptr + n_seg);
-  ED_CATCH
-}
-
 int ed_oprep_set_kernel(ed_oprep* oprep, int32_t which) {
   ED_TRY
   ED_REQUIRE(oprep, ED_ERR_ARGUMENT, "null argument");
@@ -243,14 +183,12 @@ int ed_oprep_set_kernel(ed_oprep* oprep, int32_t which) {
 }
 
 static void apply_dispatch(ed_oprep* o, void* out, const void* x, int dtype, int side, int accumulate, double* alpha_dot) {
-  if (o->csr[side] && o->kernel_choice != 1 && o->x_seg_ptr.empty()) {   // cached matrix: bandwidth-bound SpMV
+  if (o->csr[side] && o->kernel_choice != 1) {   // cached matrix: bandwidth-bound SpMV
     if (o->rbasis) ED_REQUIRE(dtype == ED_C128, ED_ERR_ARGUMENT, "a reduced operator representation is ComplexF64: vectors must be ED_C128");
     ed_apply_csr(o, out, x, dtype, side, accumulate, alpha_dot);
     return;
   }
   const bool fast = !o->rbasis && o->kernel_choice == 0 && ed_apply_u1_supported(o, dtype, side);
-  ED_REQUIRE(o->x_seg_ptr.empty() || fast, ED_ERR_UNSUPPORTED,
-             "segmented input vectors (ed_oprep_set_x_segments) are only consumed by the U(1) fast-path kernel");
   if (o->rbasis) {
     ED_REQUIRE(dtype == ED_C128, ED_ERR_ARGUMENT, "a reduced operator representation is ComplexF64: vectors must be ED_C128");
     ed_apply_reduced(o, out, x, side, accumulate, alpha_dot);
@@ -291,7 +229,7 @@ int ed_apply(ed_oprep* oprep, void* out, int64_t n_out, const void* x, int64_t n
 int ed_apply_async(ed_oprep* oprep, void* out, const void* x, int32_t dtype, int32_t side, int32_t accumulate,
                    double* alpha_dot) {
   ED_TRY
-  ED_REQUIRE(oprep && out && (x || !oprep->x_seg_ptr.empty()), ED_ERR_ARGUMENT, "null argument");
+  ED_REQUIRE(oprep && out && x, ED_ERR_ARGUMENT, "null argument");
   ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "dtype must be ED_F64 or ED_C128");
   ED_REQUIRE(!(oprep->is_complex && dtype == ED_F64), ED_ERR_ARGUMENT,
              "a complex operator representation needs ComplexF64 vectors");

@@ -81,12 +81,6 @@ k6_apply_reduced(LookupDesc L, SymDesc S, RLookupDesc R, int64_t row_lo, int64_t
 
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot) {
   // large row ranges: word-parallel orbit sweep (reduced_staged.cu); small ones: the simple row-per-thread kernel below
-  // opt-in experiment: warp-per-row kernel exploiting g(b xor f) = g(b) xor g(f) (reduced_linear.cu); default for
-  // large row ranges: the staged word-parallel sweep (reduced_staged.cu); else the simple row-per-thread kernel below
-  if (ed_apply_reduced_linear_supported(o)) {
-    ed_apply_reduced_linear(o, out, x, side, accumulate, alpha_dot);
-    return;
-  }
   static const bool force_simple = getenv("EDCUDA_K6_SIMPLE") != nullptr;
   if (!force_simple && ed_apply_reduced_staged_supported(o)) {
     ed_apply_reduced_staged(o, out, x, side, accumulate, alpha_dot);
@@ -113,7 +107,7 @@ void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accum
   R.dim = rb->dim;
   const int block = 128;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + block - 1) / block, (int64_t)ed_sm_count() * 16));
-  static thread_local DevBuf<double> partial_buf;
+  DevBuf<double>& partial_buf = ed_scratch<double, 3>();
   double* partials = nullptr;
   if (alpha_dot) {
     if (partial_buf.n < (size_t)2 * grid) partial_buf.alloc((size_t)2 * grid);

@@ -331,8 +331,8 @@ struct K6Scratch {
 };
 
 static K6Scratch& scratch() {
-  static thread_local K6Scratch s;
-  return s;
+  static thread_local K6Scratch s[16];     // per device (one process may drive several GPUs)
+  return s[ed_current_device() & 15];
 }
 
 // Phases A + B for rows [row0, row0 + nb): sc.offs = exclusive offsets of the off-diagonal hits per row, sc.words = the

@@ -10,6 +10,15 @@ static cudaStream_t g_own_stream[64] = {nullptr};
 
 void ed_set_error(const std::string& msg) { t_last_error = msg; }
 
+// internal, nestable by one level: the multi-GPU context runs each rank's work on that rank's stream
+static thread_local cudaStream_t t_saved_stream = nullptr;
+static thread_local bool t_saved_use = false;
+void ed_push_stream(cudaStream_t s) {
+  t_saved_stream = t_user_stream; t_saved_use = t_use_user_stream;
+  t_user_stream = s; t_use_user_stream = true;
+}
+void ed_pop_stream() { t_user_stream = t_saved_stream; t_use_user_stream = t_saved_use; }
+
 void ed_require_device() {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -37,6 +46,12 @@ bool ed_is_device_pointer(const void* p) {
     return false;
   }
   return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int ed_current_device() {
+  int dev = 0;
+  ED_CUDA(cudaGetDevice(&dev));
+  return dev;
 }
 
 int ed_sm_count() {
@@ -136,7 +151,7 @@ int ed_set_stream(void* cuda_stream, int32_t enable) {
 
 int64_t ed_kernel_launch_count(void) { return g_launch_count.load(); }
 
-// ---- device buffers that can be shared between the per-GPU processes of one node (CUDA IPC over NVLink) ----
+// ---- plain device buffers owned by the caller ----
 int ed_device_malloc(int64_t bytes, void** ptr) {
   ED_TRY
   ED_REQUIRE(ptr && bytes >= 0, ED_ERR_ARGUMENT, "bad arguments");
@@ -152,35 +167,10 @@ int ed_device_free(void* ptr) {
   ED_CATCH
 }
 
-int ed_ipc_get_handle(void* dev_ptr, uint8_t* handle64) {
-  ED_TRY
-  ED_REQUIRE(dev_ptr && handle64, ED_ERR_ARGUMENT, "null argument");
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  cudaIpcMemHandle_t h;
-  ED_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
-  memcpy(handle64, &h, 64);
-  ED_CATCH
-}
-
-int ed_ipc_open_handle(const uint8_t* handle64, void** ptr) {
-  ED_TRY
-  ED_REQUIRE(handle64 && ptr, ED_ERR_ARGUMENT, "null argument");
-  cudaIpcMemHandle_t h;
-  memcpy(&h, handle64, 64);
-  ED_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
-  ED_CATCH
-}
-
 int ed_release_staging(void) {
   ED_TRY
   for (auto& s : t_stage)
     if (!s.busy && s.p) { cudaFree(s.p); s.p = nullptr; s.cap = 0; }
-  ED_CATCH
-}
-
-int ed_ipc_close_handle(void* ptr) {
-  ED_TRY
-  if (ptr) ED_CUDA(cudaIpcCloseMemHandle(ptr));
   ED_CATCH
 }
 

@@ -502,7 +502,7 @@ void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, in
   }
   ED_REQUIRE(!(c->val_complex && dtype == ED_F64), ED_ERR_ARGUMENT, "a complex operator representation needs ComplexF64 vectors");
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 7) / 8, (int64_t)ed_sm_count() * 16));
-  static thread_local DevBuf<double> pbuf;
+  DevBuf<double>& pbuf = ed_scratch<double, 4>();
   double* partials = nullptr;
   if (alpha_dot) {
     if (pbuf.n < (size_t)2 * grid) pbuf.alloc((size_t)2 * grid);

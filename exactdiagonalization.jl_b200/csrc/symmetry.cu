@@ -100,17 +100,6 @@ void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, 
       }
     }
   }
-  // bit-level target table + flip masks for the linear (warp-per-row) reduced apply
-  std::vector<uint8_t> tgt_bit((size_t)G * 64, 0);
-  std::vector<uint64_t> flipmask(G, 0);
-  for (int g = 0; g < G; ++g) {
-    for (int bit = 0; bit < 64; ++bit) tgt_bit[(size_t)g * 64 + bit] = (uint8_t)bit;
-    for (int i = 0; i < n; ++i) {
-      int j = sym.perm[(size_t)g * n + i];
-      for (int k = 0; k < space.width[i]; ++k) tgt_bit[(size_t)g * 64 + space.offset[i] + k] = (uint8_t)(space.offset[j] + k);
-    }
-    flipmask[g] = sym.flip[g] ? space.fullmask() : 0ull;
-  }
   // ---- translation factorisation: G = union of cosets T p_j with T the n1 x n2 lattice translations ------------------
   out->tr_on = false;
   if (sym.is_group && space.bits == n && n >= 4 && n <= 60 && G >= 8 && !getenv("EDCUDA_K6_NOTR")) {
@@ -168,15 +157,19 @@ void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, 
       }
     }
   }
-  out->tgt_bit.upload(tgt_bit);
-  out->flipmask.upload(flipmask);
   out->n_chunks6 = n_chunks6;
   out->lut6.upload(lut6);
   out->n_ops = G;
   out->n_chunks = n_chunks;
   out->fullmask = space.fullmask();
   out->lut.upload(lut);
-  out->chi.upload(sym.chi);
+  {
+    // the reference never reads the first element's amplitude: basis_phases starts as ones and its loop begins at the
+    // second element (symmetry_reduce_generic.jl:47, 56-78), so the identity always contributes phase 1
+    std::vector<double> chi = sym.chi;
+    if (chi.size() >= 2) { chi[0] = 1.0; chi[1] = 0.0; }
+    out->chi.upload(chi);
+  }
   std::vector<int32_t> inv = sym.inverse;
   if ((int)inv.size() != G) inv.assign(G, 0);
   out->inverse.upload(inv);
@@ -184,6 +177,7 @@ void ed_symdev_build(const ed_space& space, const ed_symmetry& sym, double tol, 
   for (int g = 0; g < G; ++g) {
     // isapprox(ampl*sgn, one; atol=tol): |chi - 1| <= tol   (symmetry_reduce_generic.jl:62)
     double dr = sym.chi[2 * g] - 1.0, di = sym.chi[2 * g + 1];
+    if (g == 0) dr = di = 0.0;      // element 0 (identity): amplitude never read by the reference
     one[g] = std::sqrt(dr * dr + di * di) <= tol ? 1 : 0;
   }
   out->chi_is_one.upload(one);

@@ -61,9 +61,6 @@ SIGNATURES = {
     "ed_release_staging": (C.c_int, []),
     "ed_device_malloc": (C.c_int, [i64, P(vp)]),
     "ed_device_free": (C.c_int, [vp]),
-    "ed_ipc_get_handle": (C.c_int, [vp, vp]),
-    "ed_ipc_open_handle": (C.c_int, [vp, P(vp)]),
-    "ed_ipc_close_handle": (C.c_int, [vp]),
     "ed_space_create": (C.c_int, [i32, vp, vp, i32, P(vp)]),
     "ed_space_destroy": (C.c_int, [vp]),
     "ed_space_bitwidth": (C.c_int, [vp, P(i32)]),
@@ -96,10 +93,6 @@ SIGNATURES = {
     "ed_oprep_dtype": (C.c_int, [vp, P(i32)]),
     "ed_oprep_set_rows": (C.c_int, [vp, i64, i64]),
     "ed_oprep_suggest_rows": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64)]),
-    "ed_oprep_suggest_row_ranges": (C.c_int, [vp, i32, i32, i32, P(i64), P(i64), P(i32)]),
-    "ed_oprep_set_x_segments": (C.c_int, [vp, i32, vp, vp]),
-    "ed_oprep_set_exchange": (C.c_int, [vp, i32, vp, C.c_uint32]),
-    "ed_oprep_remote_rows": (C.c_int, [vp, i32, i32, P(i64), P(i64), i32, P(i64), P(i64), P(i32)]),
     "ed_oprep_set_kernel": (C.c_int, [vp, i32]),
     "ed_apply": (C.c_int, [vp, vp, i64, vp, i64, i32, i32, i32]),
     "ed_apply_async": (C.c_int, [vp, vp, vp, i32, i32, i32, vp]),
@@ -115,6 +108,31 @@ SIGNATURES = {
     "ed_vector_norm2_async": (C.c_int, [vp, i64, i32, vp]),
     "ed_vector_randn_async": (C.c_int, [vp, i64, i32, u64, i64]),
     "ed_tridiag_eigvals": (C.c_int, [vp, vp, i32, vp]),
+    "ed_vector_scale_async": (C.c_int, [vp, i64, i32, dbl]),
+    "ed_ctx_unique_id": (C.c_int, [vp]),
+    "ed_ctx_create": (C.c_int, [i32, vp, P(vp)]),
+    "ed_ctx_create_rank": (C.c_int, [i32, i32, i32, vp, P(vp)]),
+    "ed_ctx_destroy": (C.c_int, [vp]),
+    "ed_ctx_info": (C.c_int, [vp, P(i32), P(i32), P(i32), P(i32)]),
+    "ed_ctx_device_stream": (C.c_int, [vp, i32, P(i32), P(vp)]),
+    "ed_ctx_sync": (C.c_int, [vp]),
+    "ed_ctx_barrier": (C.c_int, [vp]),
+    "ed_ctx_timer_record": (C.c_int, [vp, i32]),
+    "ed_ctx_timer_elapsed": (C.c_int, [vp, i32, i32, P(dbl)]),
+    "ed_ctx_allreduce_host": (C.c_int, [vp, vp, i32, i32]),
+    "ed_sharded_create": (C.c_int, [vp, vp, i32, i32, i32, P(vp)]),
+    "ed_sharded_destroy": (C.c_int, [vp]),
+    "ed_sharded_info": (C.c_int, [vp, i32, P(i64), P(i64), P(i32), P(i32), P(i32), P(i32)]),
+    "ed_sharded_ranges": (C.c_int, [vp, i32, vp, vp]),
+    "ed_dvec_create": (C.c_int, [vp, P(vp)]),
+    "ed_dvec_destroy": (C.c_int, [vp]),
+    "ed_dvec_local": (C.c_int, [vp, i32, P(vp), P(i64)]),
+    "ed_dvec_randn": (C.c_int, [vp, u64, dbl]),
+    "ed_dvec_upload": (C.c_int, [vp, vp]),
+    "ed_dvec_download": (C.c_int, [vp, vp]),
+    "ed_apply_sharded": (C.c_int, [vp, vp, vp, i32, vp]),
+    "ed_lanczos_sharded": (C.c_int, [vp, i32, u64, vp, vp, vp, vp, i32, P(i32), P(dbl)]),
+    "ed_shard_plan_describe": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -64,6 +64,9 @@ typedef struct ed_operator ed_operator;
 typedef struct ed_symmetry ed_symmetry;
 typedef struct ed_rbasis   ed_rbasis;
 typedef struct ed_oprep    ed_oprep;
+typedef struct ed_ctx      ed_ctx;      /* multi-GPU communicator (one rank per GPU of the node) */
+typedef struct ed_sharded  ed_sharded;  /* operator representation with its rows distributed over the ranks */
+typedef struct ed_dvec     ed_dvec;     /* distributed vector: every rank holds its rows */
 
 /* ---- library ----------------------------------------------------------------------- */
 const char* ed_last_error(void);
@@ -81,14 +84,9 @@ int  ed_release_staging(void);
 /* total number of kernel launches issued by the library in this process (for bench accounting). */
 int64_t ed_kernel_launch_count(void);
 
-/* device buffers that the per-GPU processes of one node can map into each other (CUDA IPC, peer access over
- * NVLink): the row-sharded matvec reads the far-bond tiles of x straight from the owning GPU instead of
- * all-gathering the whole vector.  handle64 is a 64-byte cudaIpcMemHandle_t. */
+/* plain device buffers owned by the caller (e.g. a host language without its own CUDA binding). */
 int ed_device_malloc(int64_t bytes, void** ptr);
 int ed_device_free(void* ptr);
-int ed_ipc_get_handle(void* dev_ptr, uint8_t* handle64);
-int ed_ipc_open_handle(const uint8_t* handle64, void** ptr);
-int ed_ipc_close_handle(void* ptr);
 
 /* ---- HilbertSpace  (HilbertSpace/hilbert_space.jl:25-41, site.jl:69-93) ------------- */
 /* n_states[i] local states on site i; qn is [sum_i n_states[i]][n_qn] row-major: the quantum
@@ -184,29 +182,6 @@ int ed_oprep_set_rows(ed_oprep* oprep, int64_t row_lo, int64_t row_hi);
 /* Row range rank `rank` of `world` should own: the reference's balanced splitrange (src/util.jl:102-121) with the
  * boundaries snapped to the fast kernel's tile boundaries, so that segmented inputs (below) are tile aligned. */
 int ed_oprep_suggest_rows(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi);
-/* Like ed_oprep_suggest_rows, but a rank may receive TWO row ranges (row_lo[2], row_hi[2], *n_ranges = 2): when the
- * operator has a bond that wraps around the most significant site (the periodic bond of a ring), every rank gets the same
- * range of the remaining high bits in both halves of the basis, which keeps that bond -- otherwise an 8-byte gather from a
- * peer GPU -- rank-local.  The ranges are tile aligned; apply them one after the other with ed_oprep_set_rows.
- * *n_ranges = 1: same answer as ed_oprep_suggest_rows (second range empty).  Not in the reference (no multi-device path;
- * its threads split rows with splitrange, src/util.jl:102-121). */
-int ed_oprep_suggest_row_ranges(ed_oprep* oprep, int32_t dtype, int32_t world, int32_t rank, int64_t* row_lo, int64_t* row_hi,
-                                int32_t* n_ranges);
-/* Split exchange for segmented inputs.  mode 1 (local pass): neighbour tiles that live in a segment outside
- * local_segment_mask (bit s = segment s is this process's own memory) are skipped; mode 2 (remote pass): only those
- * tiles are read -- from `mirror`, a full-length local vector into which the caller copied the rows listed by
- * ed_oprep_remote_rows (copy engines over NVLink, concurrently with the local pass) -- and added to `out`; with a dot
- * pointer each pass returns its own part of <x, Hx>.  mode 0 (default): one pass, peers read through the segments. */
-int ed_oprep_set_exchange(ed_oprep* oprep, int32_t mode, const void* mirror, uint32_t local_segment_mask);
-/* Rows of x outside the row ranges [row_lo[i], row_hi[i]) that the fast kernel reads when it applies those ranges
- * (whole neighbour tiles, ascending, merged).  Two-call protocol: out_lo = out_hi = NULL returns the count in *n_out. */
-int ed_oprep_remote_rows(ed_oprep* oprep, int32_t dtype, int32_t n_ranges, const int64_t* row_lo, const int64_t* row_hi,
-                         int32_t capacity, int64_t* out_lo, int64_t* out_hi, int32_t* n_out);
-/* Hand the input vector over as n_seg (<= 16) contiguous segments instead of one pointer: segment s holds rows
- * [seg_lo[s], seg_lo[s+1]) at device address seg_ptr[s] (local memory or a peer GPU's buffer opened with
- * ed_ipc_open_handle).  While set, ed_apply_async ignores its `x` argument.  n_seg = 0 clears.  Only the U(1)
- * fast-path kernel consumes segments (ED_ERR_UNSUPPORTED otherwise); boundaries must come from ed_oprep_suggest_rows. */
-int ed_oprep_set_x_segments(ed_oprep* oprep, int32_t n_seg, const int64_t* seg_lo, const void* const* seg_ptr);
 /* Choose the kernel: 0 = automatic (fastest exact path), 1 = force the generic term-walk kernel. */
 int ed_oprep_set_kernel(ed_oprep* oprep, int32_t which);
 
@@ -271,8 +246,86 @@ int ed_lanczos_update_async(void* u_prev_inout, const void* w, const void* u_cur
 int ed_vector_norm2_async(const void* v, int64_t n, int32_t dtype, double* norm2_out);
 /* v[i] = normal(0,1) from Philox keyed by (seed, global_row_offset + i): shard-count independent. */
 int ed_vector_randn_async(void* v, int64_t n, int32_t dtype, uint64_t seed, int64_t global_row_offset);
+/* v *= a (async). */
+int ed_vector_scale_async(void* v, int64_t n, int32_t dtype, double a);
 /* lowest eigenvalues of the k x k symmetric tridiagonal (alpha, beta[0..k-2]) -- host helper. */
 int ed_tridiag_eigvals(const double* alpha, const double* beta, int32_t k, double* eig_out);
+
+/* ---- multi-GPU: rows sharded over the GPUs of one node ------------------------------------------------
+ * The reference parallelises INSIDE apply! (Threads.@threads over statically split rows,
+ * Representation/abstract_operator_representation.jl:260-267, 358-378; splitrange, util.jl:102-121): callers never
+ * partition anything.  The same holds here: a context owns the streams and the NCCL communicator(s), a sharded
+ * representation owns the row partition and the exchange, and a distributed vector is addressed through the API
+ * (ascending-basis) order.  Two ways to create a context:
+ *   ed_ctx_create       ONE process drives n_gpus devices (ncclCommInitAll; peer access between the devices).  All
+ *                       device ids equal = "loopback": the ranks share one GPU and the collectives are emulated with
+ *                       stream-ordered kernels (no NCCL) -- for testing the world > 1 logic on a single GPU.
+ *   ed_ctx_create_rank  one process per GPU (torchrun / mpirun): rank 0 calls ed_ctx_unique_id, the launcher broadcasts
+ *                       the 128 bytes, every process joins with its rank (ncclCommInitRank; buffers through CUDA IPC).
+ * Every function below that takes a context-bound handle is COLLECTIVE: all processes call it in the same order.
+ * Per-rank arguments are arrays over the LOCAL ranks of the calling process (n_gpus entries, or 1). */
+int ed_ctx_unique_id(uint8_t* uid128);
+int ed_ctx_create(int32_t n_gpus, const int32_t* device_ids /* NULL: 0..n_gpus-1 */, ed_ctx** out);
+int ed_ctx_create_rank(int32_t world, int32_t rank, int32_t device, const uint8_t* uid128, ed_ctx** out);
+int ed_ctx_destroy(ed_ctx* ctx);
+/* any output may be NULL; nccl_version = 0 when no NCCL communicator exists (world 1 or loopback). */
+int ed_ctx_info(const ed_ctx* ctx, int32_t* world, int32_t* n_local, int32_t* first_rank, int32_t* nccl_version);
+/* device and cudaStream_t of local rank `local_index`: all asynchronous work of the context runs on that stream. */
+int ed_ctx_device_stream(const ed_ctx* ctx, int32_t local_index, int32_t* device, void** cuda_stream);
+int ed_ctx_sync(ed_ctx* ctx);       /* host waits for this process's ranks */
+int ed_ctx_barrier(ed_ctx* ctx);    /* stream-ordered barrier over all ranks, then ed_ctx_sync */
+/* CUDA-event timing on the ranks' streams: record into slot 0..61, then elapsed = MAX over all ranks (milliseconds). */
+int ed_ctx_timer_record(ed_ctx* ctx, int32_t slot);
+int ed_ctx_timer_elapsed(ed_ctx* ctx, int32_t slot_a, int32_t slot_b, double* ms_max);
+/* in-place all-reduce of up to 4 host doubles over the PROCESSES of the context (op 0 = sum, 1 = max). */
+int ed_ctx_allreduce_host(ed_ctx* ctx, double* values, int32_t count, int32_t op);
+
+/* opreps[i] = the representation created on local rank i's device (same operator and basis everywhere).
+ * exchange: 0 = automatic, 1 = NCCL all-gather of x per matvec (contiguous row ranges; any representation),
+ *           2 = halo copies (tiled U(1) kernel only): every rank owns whole kernel tiles, the peer tiles it reads are
+ *               copied by the copy engines over NVLink into a compact halo buffer in n_chunks pieces, each kernel chunk
+ *               waiting only for its own piece.  Automatic = 2 where supported.  n_chunks <= 0: default (8). */
+int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32_t exchange, int32_t n_chunks, ed_sharded** out);
+int ed_sharded_destroy(ed_sharded* sh);
+/* rows owned by local rank `local_index`, elements it copies from peers per matvec, number of its global row ranges,
+ * peer copies and launch chunks per matvec, and whether the halo exchange is in use.  Outputs may be NULL. */
+int ed_sharded_info(const ed_sharded* sh, int32_t local_index, int64_t* n_local, int64_t* n_halo, int32_t* n_ranges,
+                    int32_t* n_pulls, int32_t* n_chunks, int32_t* halo_exchange);
+/* the global row ranges [row_lo[k], row_hi[k]) of that rank, ascending; its local vectors store them back to back. */
+int ed_sharded_ranges(const ed_sharded* sh, int32_t local_index, int64_t* row_lo, int64_t* row_hi);
+
+int ed_dvec_create(ed_sharded* sh, ed_dvec** out);     /* zero-filled */
+int ed_dvec_destroy(ed_dvec* v);                        /* ranks unmap their peers' buffers before the owners free them */
+int ed_dvec_local(ed_dvec* v, int32_t local_index, void** dev_ptr, int64_t* n_local);
+/* v[row] = scale * normal(0,1) from Philox keyed by (seed, global row): independent of the number of ranks. */
+int ed_dvec_randn(ed_dvec* v, uint64_t seed, double scale);
+/* host_full: full-length vector in basis order.  upload: every process copies in the rows its ranks own;
+ * download: every process writes the rows its ranks own and leaves the others untouched. */
+int ed_dvec_upload(ed_dvec* v, const void* host_full);
+int ed_dvec_download(ed_dvec* v, void* host_full);
+
+/* y = H x over all ranks (mul!), asynchronous on the ranks' streams unless dot_out (host double[2]) is given, which then
+ * receives <x, Hx> summed over all rows.  no_fence != 0 skips the stream-ordered barrier that publishes x to the peers
+ * (allowed when a collective already ran on every rank's stream after x was last written). */
+int ed_apply_sharded(ed_sharded* sh, ed_dvec* y, ed_dvec* x, int32_t no_fence, double* dot_out);
+/* ed_lanczos over the shards: Krylov vectors stay distributed and device resident, the two scalars of every step are
+ * all-reduced (NCCL), no host synchronisation inside the loop.  v0 NULL = Philox vector from seed.  ms_per_step (may
+ * be NULL) = device time per step, max over ranks. */
+int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* v0, double* alpha, double* beta,
+                       double* ritz, int32_t n_ritz, int32_t* steps_done, double* ms_per_step);
+
+/* Host-only description (no GPU needed) of rank `rank`'s share of the halo-exchange layout for operator `op` on the
+ * n_set-particle sector of n_bits spin-1/2 sites (policy 0 = planner's choice, 1 = ascending row ranges, 2 = wrap-aware
+ * ranges, 3 = best popcount ordering).
+ * counts[10] = {rows, halo rows, ranges, tiles, pulls, reads, chunks, dim, packs, send rows}.
+ * Optional outputs (NULL to skip): ranges[2*ranges] = (lo, hi);
+ * tiles[4*tiles] = (global first row, rows, local offset, launch chunk), in launch order;
+ * pulls[5*pulls] = (peer, chunk, offset in the PEER'S SEND BUFFER, offset in the halo, rows);
+ * packs[3*packs] = (offset in this rank's vector, offset in its send buffer, rows);
+ * reads[4*reads] = (tile index, global first row of the tile it reads, rows, where: offset | 1<<62 if in the halo). */
+int ed_shard_plan_describe(const ed_operator* op, int32_t n_bits, int32_t n_set, int32_t dtype, int32_t world, int32_t rank,
+                           int32_t n_chunks, int32_t policy, int64_t* counts, int64_t* ranges, int64_t* tiles,
+                           int64_t* pulls, int64_t* packs, int64_t* reads);
 
 #ifdef __cplusplus
 }

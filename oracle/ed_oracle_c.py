@@ -7,6 +7,31 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "libed_oracle.so")
+BUILD = "portable (-O3 -fopenmp, built in the build container)"
+
+
+def _native_build():
+    """bench.py's CPU arms set ED_ORACLE_NATIVE=1: rebuild the twin on the machine that runs it with -march=native
+    (BASELINE.md section 3 promises that for the timed CPU baseline); the portable prebuilt library is the fallback."""
+    import subprocess
+    out_dir = os.path.join(_HERE, "_native")
+    out = os.path.join(out_dir, "libed_oracle_native.so")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        src = os.path.join(_HERE, "ed_oracle_c.c")
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-shared", "-fPIC", "-o", out + ".tmp%d" % os.getpid(), src],
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            os.replace(out + ".tmp%d" % os.getpid(), out)
+        return out
+    except Exception:
+        return None
+
+
+if os.environ.get("ED_ORACLE_NATIVE") == "1":
+    _n = _native_build()
+    if _n:
+        _PATH, BUILD = _n, "native (-O3 -march=native -fopenmp, built on this host)"
 if not os.path.exists(_PATH):
     raise ImportError(f"{_PATH} missing: run `make -C oracle`")
 _lib = C.CDLL(_PATH)

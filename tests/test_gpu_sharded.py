@@ -1,0 +1,253 @@
+"""The multi-GPU path through the C ABI (ed_ctx_*, ed_sharded_*, ed_dvec_*, ed_apply_sharded, ed_lanczos_sharded):
+no torch.distributed anywhere on the data path.
+
+  * "loopback" contexts put world = 2..8 ranks on ONE GPU (collectives emulated by stream-ordered kernels): the whole
+    partition / pack / pull / chunked-launch logic runs on the driver's single-GPU box and is compared with the oracle;
+  * with >= 2 GPUs the same checks run over NCCL: one process driving all GPUs (ed_ctx_create, ncclCommInitAll) and one
+    process per GPU (ed_ctx_create_rank, NCCL unique id broadcast by the launcher, send buffers through CUDA IPC).
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import ed_oracle as O
+import ed_oracle_c as OC
+from helpers import oracle_spin_chain, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _model(ed, n, model):
+    L = ed.lattices
+    hs, pauli = ed.spin_half_system(n)
+    if model == "xxz":
+        return hs, ed.models.xxz_bonds(hs, L.chain_bonds(n), 1.0, 0.37)
+    if model == "j1j2":
+        return hs, ed.simplify(ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 1)) + ed.models.heisenberg_bonds(hs, L.chain_bonds(n, 2), 0.5))
+    if model == "open":
+        return hs, ed.models.xxz_bonds(hs, L.chain_bonds(n, 1, periodic=False), 0.8, -1.1)
+    if model == "square":
+        return hs, ed.models.heisenberg_bonds(hs, L.square_bonds(4, n // 4))
+    raise ValueError(model)
+
+
+def _check_sharded(ed, ctx, n, n_dn, model, exchange="auto", n_chunks=0, cplx=False, generic=False, lanczos_steps=0):
+    from edcuda.distributed import ShardedOperator
+    hs, h = _model(ed, n, model)
+
+    def make():
+        opr = ed.represent(ed.represent(ed.HilbertSpaceSector(hs, n - 2 * n_dn)), h)
+        return opr.set_kernel(1) if generic else opr
+
+    sh = ShardedOperator(ctx, make, dtype=np.complex128 if cplx else np.float64, exchange=exchange, n_chunks=n_chunks)
+    d = sh.dimension
+    basis = OC.basis_fixed_popcount(n, n_dn)
+    assert d == len(basis)
+    rng = np.random.default_rng(n + n_dn)
+    x = rng.standard_normal(d) + (1j * rng.standard_normal(d) if cplx else 0.0)
+    exp = np.zeros_like(x)
+    OC.apply(basis, h.arrays(), x, exp)
+    # the ranges of the local ranks are disjoint and, in a single-process context, cover the basis
+    cover = np.zeros(d, dtype=np.int32)
+    for i in range(ctx.n_local):
+        info = sh.info(i)
+        rg = sh.ranges(i)
+        assert sum(hi - lo for lo, hi in rg) == info["n_local"]
+        for lo, hi in rg:
+            cover[lo:hi] += 1
+    if ctx.n_local == ctx.world:
+        assert np.all(cover == 1)
+    xv, yv = sh.vector(), sh.vector()
+    xv.upload(x)
+    assert np.array_equal(xv.download()[cover == 1], x[cover == 1])
+    dot = sh.apply(yv, xv, dot=True)
+    y = yv.download()
+    scale = np.max(np.abs(exp))
+    assert np.max(np.abs(y - exp)[cover == 1]) / scale < TOL
+    assert abs(dot - np.vdot(x, exp)) < 1e-10 * np.linalg.norm(x) * np.linalg.norm(exp)
+    # twice more without re-uploading (send buffers alternate), then y -> x -> y chains like a solver
+    sh.apply(yv, xv)
+    sh.apply(xv, yv)
+    exp2 = np.zeros_like(x)
+    OC.apply(basis, h.arrays(), exp, exp2)
+    x2 = xv.download()
+    assert np.max(np.abs(x2 - exp2)[cover == 1]) / np.max(np.abs(exp2)) < TOL
+    out = dict(info=sh.info(0), cover=cover)
+    if lanczos_steps:
+        res = sh.lanczos(lanczos_steps, seed=11)
+        out["lanczos"] = res
+    xv.close(); yv.close(); sh.close()
+    return out
+
+
+@pytest.mark.parametrize("n,n_dn,model,world,chunks", [(20, 10, "xxz", 2, 0), (22, 11, "xxz", 4, 3), (20, 7, "j1j2", 3, 2),
+                                                       (18, 9, "open", 2, 1), (24, 12, "xxz", 8, 8), (16, 8, "square", 4, 4)])
+def test_loopback_halo_exchange_vs_c_oracle(gpu_ed, n, n_dn, model, world, chunks):
+    """world ranks on one GPU: planner's partition, owner-side packing, per-chunk pulls into the halo, chunked launches."""
+    ed = gpu_ed
+    from edcuda.distributed import Context
+    ctx = Context.single_process([0] * world)
+    assert ctx.world == world and ctx.n_local == world and ctx.nccl_version == 0
+    out = _check_sharded(ed, ctx, n, n_dn, model, n_chunks=chunks)
+    assert out["info"]["exchange"] == "halo"
+    ctx.close()
+
+
+def test_loopback_complex_vectors_and_allgather_and_generic(gpu_ed):
+    ed = gpu_ed
+    from edcuda.distributed import Context
+    ctx = Context.single_process([0, 0, 0])
+    assert _check_sharded(ed, ctx, 20, 10, "xxz", cplx=True)["info"]["exchange"] == "halo"
+    assert _check_sharded(ed, ctx, 20, 10, "xxz", exchange="allgather")["info"]["exchange"] == "allgather"   # north_star's exchange
+    assert _check_sharded(ed, ctx, 16, 8, "xxz", generic=True)["info"]["exchange"] == "allgather"            # term-walk kernel
+    ctx.close()
+
+
+def test_loopback_world1_and_lanczos_matches_single_gpu(gpu_ed, golden):
+    ed = gpu_ed
+    from edcuda.distributed import Context, ShardedOperator
+    from edcuda.lanczos import lanczos
+    hs, h = ed.models.heisenberg_chain(16)
+    ref = lanczos(ed.represent(ed.represent(ed.HilbertSpaceSector(hs, 0)), h), 100, seed=11)
+    for devices in ([0], [0, 0], [0, 0, 0, 0]):
+        ctx = Context.single_process(devices)
+        sh = ShardedOperator(ctx, lambda: ed.represent(ed.represent(ed.HilbertSpaceSector(hs, 0)), h))
+        res = sh.lanczos(100, seed=11)
+        assert res.steps == 100 and res.ms_per_step > 0
+        # same Philox start vector whatever the partition; the recurrence amplifies reduction-order differences slowly
+        assert np.allclose(res.alpha[:30], ref.alpha[:30], atol=1e-9) and np.allclose(res.beta[:30], ref.beta[:30], atol=1e-9)
+        assert abs(res.ritz[0] - golden["known_answers"]["L16_E0"]) < 1e-10
+        sh.close(); ctx.close()
+
+
+def test_loopback_reduced_representation_allgather(gpu_ed):
+    """config 4's machinery at a size the oracle follows: reduced representation, rows sharded, x all-gathered."""
+    ed = gpu_ed
+    from edcuda.distributed import Context, ShardedOperator
+    from helpers import to_oracle_symops
+    n = 12
+    hs, h = ed.models.heisenberg_chain(n)
+    hs_o, h_o = oracle_spin_chain(n)
+    symops = ed.lattices.chain_translation_irrep(n, 5)
+    rhsr_o = O.symmetry_reduce(O.represent(O.HilbertSpaceSector(hs_o, 0)), to_oracle_symops(symops))
+    ropr_o = O.ReducedOperatorRepresentation(rhsr_o, h_o)
+    for cached in (False, True):
+        ctx = Context.single_process([0, 0, 0])
+
+        def make():
+            ropr = ed.represent(ed.symmetry_reduce(ed.represent(ed.HilbertSpaceSector(hs, 0)), symops), h)
+            ropr._keep = ropr.reduced_hilbert_space_representation
+            return ropr
+
+        sh = ShardedOperator(ctx, make)
+        if cached:
+            for o in sh.oprs:
+                o.cache_matrix()
+        d = sh.dimension
+        assert d == rhsr_o.dimension and sh.info(0)["exchange"] == "allgather"
+        rng = np.random.default_rng(3)
+        x = rng.standard_normal(d) + 1j * rng.standard_normal(d)
+        xv, yv = sh.vector(), sh.vector()
+        xv.upload(x)
+        sh.apply(yv, xv)
+        exp = O.apply_serial(np.zeros(d, dtype=complex), ropr_o, x, "left")
+        assert rel_err(yv.download(), exp) < TOL
+        xv.close(); yv.close(); sh.close(); ctx.close()
+
+
+def test_sharded_argument_errors(gpu_ed):
+    ed = gpu_ed
+    from edcuda.distributed import Context, ShardedOperator
+    ctx = Context.single_process([0, 0])
+    hs, pauli = ed.spin_half_system(8)
+    op = ed.simplify(pauli(0, "x") * pauli(1, "x") * pauli(2, "x") + ed.models.heisenberg_bonds(hs, ed.lattices.chain_bonds(8)))
+    with pytest.raises(ed.UnsupportedError):          # halo exchange needs the tiled kernel
+        ShardedOperator(ctx, lambda: ed.represent(ed.represent(hs), op), exchange="halo")
+    sh = ShardedOperator(ctx, lambda: ed.represent(ed.represent(hs), op))
+    other = ShardedOperator(ctx, lambda: ed.represent(ed.represent(hs), op))
+    x, y = sh.vector(), other.vector()
+    with pytest.raises(ValueError):                   # vectors of another representation
+        sh.apply(y, x)
+    with pytest.raises(ed.DimensionMismatch):
+        x.upload(np.zeros(3))
+    x.close(); y.close(); sh.close(); other.close(); ctx.close()
+    with pytest.raises(ValueError):
+        Context.single_process([])
+
+
+# ------------------------------------------------------------------ NCCL (>= 2 GPUs)
+def test_nccl_single_process_context(gpu_ed):
+    """ed_ctx_create(n_gpus, device_ids): one process drives every GPU, ncclCommInitAll, direct peer pointers."""
+    ed = gpu_ed
+    from edcuda.distributed import Context
+    n_gpu = min(ed.device_count(), 4)
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    ctx = Context.single_process(list(range(n_gpu)))
+    assert ctx.nccl_version > 0
+    out = _check_sharded(ed, ctx, 24, 12, "xxz", lanczos_steps=60)
+    assert out["info"]["exchange"] == "halo"
+    _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
+    ctx.close()
+
+
+def _rank_worker(rank, world, port, q):
+    try:
+        os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        import sys
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        for p in (os.path.join(root, "exactdiagonalization.jl_b200"), os.path.join(root, "oracle"), os.path.dirname(__file__)):
+            sys.path.insert(0, p)
+        import edcuda as ed
+        from edcuda.distributed import Context
+        ctx = Context.from_env()
+        assert ctx.world == world and ctx.n_local == 1 and ctx.rank == rank
+        out = _check_sharded(ed, ctx, 24, 12, "xxz", lanczos_steps=60)
+        out2 = _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
+        ctx.barrier()
+        ctx.close()
+        q.put(("ok", rank, out["lanczos"].alpha, out["lanczos"].ritz, int(out["cover"].sum()), out["info"]))
+    except Exception:
+        import traceback
+        q.put(("error", rank, traceback.format_exc()))
+
+
+def test_nccl_process_per_gpu_context(gpu_ed):
+    """ed_ctx_create_rank: one process per GPU, NCCL unique id handed out by the launcher's store, IPC send buffers."""
+    ed = gpu_ed
+    import torch.multiprocessing as mp
+    from edcuda.lanczos import lanczos
+    world = min(ed.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_rank_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    msgs = []
+    try:
+        for _ in range(world):
+            msgs.append(q.get(timeout=300))
+            if msgs[-1][0] != "ok":
+                break
+    except Exception:
+        msgs.append(("error", -1, "no rank reported within 300 s"))
+    if any(m[0] != "ok" for m in msgs):
+        for p in procs:
+            p.terminate()
+        bad = [m for m in msgs if m[0] != "ok"][0]
+        pytest.fail(f"rank {bad[1]} failed:\n{bad[2]}")
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    hs, h = _model(ed, 24, "xxz")
+    ref = lanczos(ed.represent(ed.represent(ed.HilbertSpaceSector(hs, 0)), h), 60, seed=11)
+    assert sum(m[4] for m in msgs) == 2704156     # C(24, 12): the ranks' rows tile the basis
+    for m in msgs:
+        assert np.allclose(m[2][:25], ref.alpha[:25], atol=1e-9) and abs(m[3][0] - ref.ritz[0]) < 1e-9
+        assert m[5]["exchange"] == "halo"

@@ -401,11 +401,15 @@ def main():
         def step():
             check(lib.ed_apply_async(opr._handle, y.data_ptr(), x.data_ptr(), ed.ED_F64, 0, 0, None))
 
+        sampler = ClockSampler(local_rank)
+        sampler.start()                       # nvidia-smi needs ~0.2 s to deliver its first sample: it runs from the warm-up on
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        t_w = time.perf_counter()
+        while not sampler.samples and time.perf_counter() - t_w < 3.0:     # same load as the timed steps
+            step()
+            torch.cuda.synchronize()
         launches0 = ed.kernel_launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
@@ -428,12 +432,19 @@ def main():
         info = sh.info(0)
         xv, yv = sh.vector(), sh.vector()
         xv.randn(seed, 1.0 / math.sqrt(dim))
-        for _ in range(args.warmup):
-            sh.apply(yv, xv)
-        ctx.barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            sh.apply(yv, xv)
+        ctx.barrier()
+        for _ in range(40):                   # keep the load up until nvidia-smi has delivered a sample (all ranks in step)
+            flag = ctx.allreduce([1.0 if (rank != 0 or sampler.samples) else 0.0], "sum")[0]
+            if flag >= world:
+                break
+            for _ in range(5):
+                sh.apply(yv, xv)
+            ctx.barrier()
         launches0 = ed.kernel_launch_count()
         ctx.timer_record(0)
         for _ in range(args.steps):

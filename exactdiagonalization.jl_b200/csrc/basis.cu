@@ -291,6 +291,8 @@ int ed_basis_generate(const ed_space* space, const int64_t* allowed_qn, int64_t 
   b->space = *space;
   b->br_bits = br_bits;
   const ed_space& sp = b->space;
+  b->gen_n_allowed = n_allowed < 0 ? -1 : n_allowed;
+  if (n_allowed > 0) b->gen_allowed.assign(allowed_qn, allowed_qn + n_allowed * sp.n_qn);
   if (n_allowed < 0) {
     if (sp.all_pow2) {
       ED_REQUIRE(sp.bits <= 62, ED_ERR_UNSUPPORTED, "full space too large");

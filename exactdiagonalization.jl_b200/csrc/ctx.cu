@@ -129,6 +129,14 @@ void loop_join(ed_ctx* c) {
       if (&o != &r) ED_CUDA(cudaStreamWaitEvent(r.stream, o.ev, 0));
 }
 
+// loopback only: the ranks share one device and one host thread, hence also the library's per-thread, per-device scratch
+// buffers (reduction partials, K6 staging): rank i+1's work must not start before rank i's is done
+void loop_chain(ed_ctx* c, size_t i) {
+  if (!c->loopback || i + 1 >= c->local.size()) return;
+  ED_CUDA(cudaEventRecord(c->local[i].ev, c->local[i].stream));
+  ED_CUDA(cudaStreamWaitEvent(c->local[i + 1].stream, c->local[i].ev, 0));
+}
+
 // in-place all-reduce of `count` doubles held at bufs[i] on local rank i (op 0 = sum, 1 = max), stream ordered
 void ctx_allreduce(ed_ctx* c, const std::vector<double*>& bufs, int count, int op) {
   if (c->world == 1) return;
@@ -350,6 +358,7 @@ void sharded_apply(ed_sharded* S, ed_dvec* y, ed_dvec* x, bool packed, bool want
       } else if (want_dot) {
         ED_CUDA(cudaMemsetAsync(Q.dot.p, 0, 2 * sizeof(double), c->local[i].stream));
       }
+      loop_chain(c, i);
     }
   }
   if (want_dot) {
@@ -860,6 +869,7 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
     RankScope scope(c->local[i]);
     const int rc = ed_vector_norm2_async(u_cur->local[i], sh->r[i].n_local, sh->dtype, norms[i].p);
     ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
+    loop_chain(c, i);
   }
   sharded_pack(sh, u_cur);         // before the all-reduce: the collective doubles as the fence that publishes the pack
   allreduce_at(norms, 0);
@@ -876,6 +886,7 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
       const int rc = ed_lanczos_update_async(u_prev->local[i], w->local[i], u_cur->local[i], sh->r[i].n_local, sh->dtype, dots[i].p + 2 * j,
                                              norms[i].p + 2 * j, j > 0 ? norms[i].p + 2 * (j - 1) : nullptr, norms[i].p + 2 * (j + 1));
       ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
+      loop_chain(c, i);
     }
     std::swap(u_cur, u_prev);
     if (j + 1 < n_steps) sharded_pack(sh, u_cur);

@@ -183,6 +183,9 @@ struct ed_basis {
   DevBuf<uint64_t> dp_prefix;
   DevBuf<int32_t> dp_next;
   DevBuf<uint8_t> dp_accept, site_off, site_w, site_ns;
+  // how the basis was made (checkpoints regenerate sector bases from this instead of storing words)
+  int64_t gen_n_allowed = -2;            // -2: user list, -1: whole space, >= 0: sector with these allowed tuples
+  std::vector<int64_t> gen_allowed;
   LookupDesc desc() const;
   void materialize();  // generate `words` on device if not present (K1)
 };
@@ -348,6 +351,7 @@ void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunk
 void ed_apply_u1_sharded(ed_oprep* o, int dtype, const U1ShardLaunch& L);
 void ed_reduce_pairs(const double* partials, int n, double* out2);                              // apply.cu
 int ed_lanczos_finish(const double* hd, const double* hn, int n_steps, double* alpha, double* beta, double* ritz, int n_ritz);   // lanczos.cu
+void ed_rbasis_finish_index(ed_rbasis* r);                                                      // symmetry.cu: bucket index over the words
 void ed_push_stream(cudaStream_t s);    // runtime.cu: run this thread's library work on s until ed_pop_stream()
 void ed_pop_stream();
 void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accumulate,

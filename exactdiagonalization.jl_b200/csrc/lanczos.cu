@@ -324,37 +324,15 @@ int ed_lanczos(ed_oprep* oprep, int32_t n_steps, const void* v0, int32_t dtype, 
   ED_TRY
   ED_REQUIRE(oprep && alpha && beta, ED_ERR_ARGUMENT, "null argument");
   ED_REQUIRE(n_steps >= 1, ED_ERR_ARGUMENT, "n_steps must be positive");
-  ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
-  ED_REQUIRE(!(oprep->is_complex && dtype == ED_F64), ED_ERR_ARGUMENT, "a complex operator representation needs ComplexF64 vectors");
-  ED_REQUIRE(oprep->row_lo == 0 && oprep->row_hi == oprep->dim, ED_ERR_ARGUMENT,
-             "ed_lanczos drives an unsharded representation; use the host-layer loop for row shards");
-  ed_require_device();
-  const int64_t n = oprep->dim;
-  ED_REQUIRE(n >= 1, ED_ERR_ARGUMENT, "empty representation");
-  const size_t es = dtype == ED_C128 ? 16 : 8;
-  DevBuf<unsigned char> bufA(n * es), bufB(n * es), bufW(n * es);
-  DevBuf<double> dots((size_t)2 * n_steps), norms((size_t)2 * (n_steps + 1));
-  void* u_cur = bufA.p;
-  void* u_prev = bufB.p;
-  ED_CUDA(cudaMemsetAsync(u_prev, 0, n * es, ed_stream()));
-  if (v0) {
-    ED_CUDA(cudaMemcpyAsync(u_cur, v0, n * es, ed_is_device_pointer(v0) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ed_stream()));
-  } else {
-    ED_REQUIRE(ed_vector_randn_async(u_cur, n, dtype, seed, 0) == ED_OK, ED_ERR_INTERNAL, ed_last_error());
-  }
-  vector_norm2(u_cur, n, dtype, norms.p);
-  for (int j = 0; j < n_steps; ++j) {
-    int rc = ed_apply_async(oprep, bufW.p, u_cur, dtype, ED_SIDE_LEFT, 0, dots.p + 2 * j);
-    ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
-    lanczos_update(u_prev, bufW.p, u_cur, n, dtype, dots.p + 2 * j, norms.p + 2 * j, j > 0 ? norms.p + 2 * (j - 1) : nullptr,
-                   norms.p + 2 * (j + 1));
-    std::swap(u_cur, u_prev);
-  }
-  std::vector<double> hd((size_t)2 * n_steps), hn((size_t)2 * (n_steps + 1));
-  dots.download(hd.data(), hd.size());
-  norms.download(hn.data(), hn.size());
-  const int done = ed_lanczos_finish(hd.data(), hn.data(), n_steps, alpha, beta, ritz, n_ritz);
-  if (steps_done) *steps_done = done;
+  // the resumable state object (checkpoint.cu) run in one go
+  ed_lanczos_state* st = nullptr;
+  int rc = ed_lanczos_state_create(oprep, dtype, v0, seed, &st);
+  ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
+  struct Guard { ed_lanczos_state* s; ~Guard() { ed_lanczos_state_destroy(s); } } guard{st};
+  rc = ed_lanczos_state_step(st, n_steps);
+  ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
+  rc = ed_lanczos_state_result(st, n_steps, alpha, beta, ritz, n_ritz, steps_done);
+  ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
   ED_CATCH
 }
 

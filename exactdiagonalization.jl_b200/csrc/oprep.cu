@@ -120,6 +120,17 @@ int ed_oprep_create(ed_basis* basis, const ed_operator* op, ed_oprep** out) {
 int ed_oprep_create_reduced(ed_rbasis* rbasis, const ed_operator* op, ed_oprep** out) {
   ED_TRY
   ED_REQUIRE(rbasis && op && out, ED_ERR_ARGUMENT, "null argument");
+  // The reduced matrix elements a * amp[col] / amp[row] (reduced_operator_representation.jl:57-116) are those of the
+  // projected operator only if the operator commutes with every symmetry element; the reference leaves that check to the
+  // caller (isinvariant, Symmetry/symmetry_apply.jl:110-135) and silently returns a wrong matrix otherwise.  Checked here,
+  // on the host, before any kernel is launched (EDCUDA_SKIP_INVARIANCE_CHECK=1 restores the reference's behaviour).
+  if (!getenv("EDCUDA_SKIP_INVARIANCE_CHECK")) {
+    int32_t inv = 1, bad = -1;
+    const int rc = ed_operator_isinvariant(&rbasis->parent->space, &rbasis->sym, op, rbasis->tol, &inv, &bad);
+    ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
+    ED_REQUIRE(inv, ED_ERR_ARGUMENT, "the operator is not invariant under symmetry element " + std::to_string(bad) +
+                                         " (isinvariant, Symmetry/symmetry_apply.jl:110-135): its reduced representation is not defined");
+  }
   std::unique_ptr<ed_oprep> o(new ed_oprep());
   o->basis = rbasis->parent;
   o->rbasis = rbasis;

@@ -319,9 +319,14 @@ static void build_rbasis(ed_rbasis* r) {
   d_err.download(&err, 1);
   ED_REQUIRE(err == 0, ED_ERR_KEY, "a symmetry image of a representative is not in the parent basis (KeyError in the reference)");
   r->dim = used;
+  ed_rbasis_finish_index(r);
+}
+
+// bucket index over the top bits of the (ascending) representatives: narrows the binary search of the reduced lookup
+void ed_rbasis_finish_index(ed_rbasis* r) {
+  const int64_t used = r->dim;
   ED_REQUIRE(used < (1ll << 32), ED_ERR_UNSUPPORTED, "reduced dimension exceeds 2^32");
-  // bucket index over the top bits
-  const int bits = parent->space.bits;
+  const int bits = r->parent->space.bits;
   int bb = std::min(bits, 22);
   while (bb > 0 && (1ll << bb) > std::max<int64_t>(4 * used, 16)) --bb;
   r->bucket_shift = bits - bb;

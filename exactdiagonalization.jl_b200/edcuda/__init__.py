@@ -9,7 +9,7 @@ from .operators import (Operator, NullOperator, simplify, pure_operator, pauli_m
 from .representation import (HilbertSpaceRepresentation, OperatorRepresentation, represent, represent_array,
                              represent_dict, apply_b, apply_serial_b, apply_parallel_b, mul_b, sparse, dimension)
 from .symmetry import (SitePermutation, GlobalBitFlip, DirectProductOperation, symmetry_apply,
-                       symmetry_apply_operator, isinvariant, symmetry_reduce, symmetry_reduce_serial,
+                       symmetry_apply_operator, isinvariant, isinvariant_all, symmetry_reduce, symmetry_reduce_serial,
                        symmetry_reduce_parallel, symmetry_reduce_b, symmetry_unreduce,
                        ReducedHilbertSpaceRepresentation, ReducedOperatorRepresentation)
 from . import lattices, models

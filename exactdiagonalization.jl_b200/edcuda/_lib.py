@@ -109,6 +109,17 @@ SIGNATURES = {
     "ed_vector_randn_async": (C.c_int, [vp, i64, i32, u64, i64]),
     "ed_tridiag_eigvals": (C.c_int, [vp, vp, i32, vp]),
     "ed_vector_scale_async": (C.c_int, [vp, i64, i32, dbl]),
+    "ed_operator_isinvariant": (C.c_int, [vp, vp, vp, dbl, P(i32), P(i32)]),
+    "ed_basis_save": (C.c_int, [vp, C.c_char_p]),
+    "ed_basis_load": (C.c_int, [vp, C.c_char_p, P(vp)]),
+    "ed_rbasis_save": (C.c_int, [vp, C.c_char_p]),
+    "ed_rbasis_load": (C.c_int, [vp, vp, dbl, C.c_char_p, P(vp)]),
+    "ed_lanczos_state_create": (C.c_int, [vp, i32, vp, u64, P(vp)]),
+    "ed_lanczos_state_destroy": (C.c_int, [vp]),
+    "ed_lanczos_state_step": (C.c_int, [vp, i32]),
+    "ed_lanczos_state_result": (C.c_int, [vp, i32, vp, vp, vp, i32, P(i32)]),
+    "ed_lanczos_state_save": (C.c_int, [vp, C.c_char_p]),
+    "ed_lanczos_state_load": (C.c_int, [vp, C.c_char_p, P(vp)]),
     "ed_ctx_unique_id": (C.c_int, [vp]),
     "ed_ctx_create": (C.c_int, [i32, vp, P(vp)]),
     "ed_ctx_create_rank": (C.c_int, [i32, i32, i32, vp, P(vp)]),

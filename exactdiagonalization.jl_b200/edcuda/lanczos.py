@@ -50,3 +50,58 @@ def lanczos(opr, n_steps: int, v0: Optional[np.ndarray] = None, seed: int = 0, d
                          n_ritz, C.byref(done)))
     k = done.value
     return LanczosResult(alpha[:k], beta[:k], ritz[: min(n_ritz, k)], k)
+
+
+class LanczosState:
+    """ed_lanczos_state: the Lanczos loop as a resumable object (run k steps, save, load, continue bit for bit)."""
+
+    def __init__(self, opr, v0: Optional[np.ndarray] = None, seed: int = 0, dtype=None, _handle=None):
+        self.opr = opr
+        if _handle is not None:
+            self._handle = _handle
+            return
+        if dtype is None:
+            dtype = np.complex128 if (opr.is_complex or (v0 is not None and np.iscomplexobj(v0))) else np.float64
+        code = ED_C128 if np.dtype(dtype) == np.complex128 else ED_F64
+        ptr = None
+        if v0 is not None:
+            v0 = np.ascontiguousarray(v0, dtype=dtype)
+            ptr = v0.ctypes.data
+        h = C.c_void_p()
+        check(lib.ed_lanczos_state_create(opr._handle, code, ptr, seed, C.byref(h)))
+        self._handle = h
+        self.steps = 0
+
+    def step(self, n_steps: int):
+        check(lib.ed_lanczos_state_step(self._handle, n_steps))
+        self.steps = getattr(self, "steps", 0) + n_steps
+        return self
+
+    def result(self, n_ritz: int = 4) -> LanczosResult:
+        cap = max(getattr(self, "steps", 0), 1)
+        alpha, beta = np.zeros(cap), np.zeros(cap)
+        n_ritz = min(n_ritz, cap)
+        ritz = np.zeros(n_ritz)
+        done = C.c_int32()
+        check(lib.ed_lanczos_state_result(self._handle, cap, alpha.ctypes.data, beta.ctypes.data, ritz.ctypes.data, n_ritz, C.byref(done)))
+        k = done.value
+        return LanczosResult(alpha[:k], beta[:k], ritz[: min(n_ritz, k)], k)
+
+    def save(self, path: str):
+        check(lib.ed_lanczos_state_save(self._handle, str(path).encode()))
+
+    @classmethod
+    def load(cls, opr, path: str, steps_taken: int):
+        h = C.c_void_p()
+        check(lib.ed_lanczos_state_load(opr._handle, str(path).encode(), C.byref(h)))
+        st = cls(opr, _handle=h)
+        st.steps = steps_taken
+        return st
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and lib is not None:
+            try:
+                lib.ed_lanczos_state_destroy(h)
+            except Exception:
+                pass

@@ -132,6 +132,17 @@ class HilbertSpaceRepresentation:
         check(lib.ed_basis_lookup(self._handle, k.ctypes.data, k.size, out.ctypes.data))
         return out
 
+    def save(self, path: str):
+        """checkpoint (ed_basis_save): sector bases store how they were generated, user lists their words"""
+        check(lib.ed_basis_save(self._handle, str(path).encode()))
+
+    @classmethod
+    def load(cls, hilbert_space, path: str):
+        base = hilbert_space.basespace()
+        h = C.c_void_p()
+        check(lib.ed_basis_load(base.handle(), str(path).encode(), C.byref(h)))
+        return cls(base, h)
+
     def __eq__(self, other):
         return (isinstance(other, HilbertSpaceRepresentation) and self.hilbert_space == other.hilbert_space
                 and self._dim == other._dim and np.array_equal(self.basis_list, other.basis_list))

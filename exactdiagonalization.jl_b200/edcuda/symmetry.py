@@ -149,6 +149,17 @@ def isinvariant(hs, symop, op: Operator) -> bool:
     return len(simplify(op - symmetry_apply_operator(hs, symop, op)).terms) == 0
 
 
+def isinvariant_all(hs, symops_and_amplitudes, op: Operator, tol: Optional[float] = None):
+    """isinvariant for every element of a symmetry at once (ed_operator_isinvariant: matrix elements compared on sample
+    words, host only, no GPU needed) -> (True, -1) or (False, index of the first violating element).
+    represent(rhsr, op) runs the same check inside the library and raises ValueError (ArgumentError)."""
+    base = hs.basespace()
+    sym = SymmetryHandle(len(base.sites), list(symops_and_amplitudes))
+    inv, bad = C.c_int32(), C.c_int32()
+    check(lib.ed_operator_isinvariant(base.handle(), sym._handle, op.handle(), -1.0 if tol is None else float(tol), C.byref(inv), C.byref(bad)))
+    return bool(inv.value), bad.value
+
+
 class ReducedHilbertSpaceRepresentation:
     """reduced_hilbert_space_representation.jl:13-22.  `basis_mapping_index` / `basis_mapping_amplitude`
     (length = parent dimension in the reference) are computed on demand by the device."""
@@ -190,6 +201,18 @@ class ReducedHilbertSpaceRepresentation:
         amp = np.empty(w.size, dtype=np.complex128)
         check(lib.ed_rbasis_mapping(self._handle, w.ctypes.data, w.size, idx.ctypes.data, amp.ctypes.data))
         return idx, amp
+
+    def save(self, path: str):
+        """checkpoint (ed_rbasis_save): representatives, orbit sizes, stabiliser marks; bound to the symmetry by a hash"""
+        check(lib.ed_rbasis_save(self._handle, str(path).encode()))
+
+    @classmethod
+    def load(cls, hsr: HilbertSpaceRepresentation, symops_and_amplitudes, path: str, tol: Optional[float] = None):
+        """skips the filter pass over the parent space; fails (ValueError) for a different space / symmetry / tolerance"""
+        sym = SymmetryHandle(len(hsr.hilbert_space.sites), list(symops_and_amplitudes))
+        h = C.c_void_p()
+        check(lib.ed_rbasis_load(hsr._handle, sym._handle, -1.0 if tol is None else float(tol), str(path).encode(), C.byref(h)))
+        return cls(hsr, h, sym)
 
     def _materialise_mapping(self):
         if self._map is None:

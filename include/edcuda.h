@@ -67,6 +67,7 @@ typedef struct ed_oprep    ed_oprep;
 typedef struct ed_ctx      ed_ctx;      /* multi-GPU communicator (one rank per GPU of the node) */
 typedef struct ed_sharded  ed_sharded;  /* operator representation with its rows distributed over the ranks */
 typedef struct ed_dvec     ed_dvec;     /* distributed vector: every rank holds its rows */
+typedef struct ed_lanczos_state ed_lanczos_state;   /* resumable Lanczos run */
 
 /* ---- library ----------------------------------------------------------------------- */
 const char* ed_last_error(void);
@@ -139,6 +140,13 @@ int ed_symmetry_destroy(ed_symmetry* sym);
 /* symmetry_apply(hs, op_g, word) for n host words: images_out[k] = g(words[k]). */
 int ed_symmetry_apply(const ed_space* space, const ed_symmetry* sym, int32_t g,
                       const uint64_t* words, int64_t n, uint64_t* images_out);
+
+/* isinvariant(hs, symop, op) for every element of `sym` (Symmetry/symmetry_apply.jl:110-135): *invariant = 1 iff
+ * <g b'| op |g b> == <b'| op |b> within tol (tol < 0: sqrt(eps)) for every element g on the sampled words b (every word of
+ * spaces up to 10 bits, 48 random words otherwise); *first_bad_element (may be NULL) = the first violating element or -1.
+ * Host only, no GPU needed.  ed_oprep_create_reduced runs it and fails with ED_ERR_ARGUMENT on a non-invariant operator. */
+int ed_operator_isinvariant(const ed_space* space, const ed_symmetry* sym, const ed_operator* op, double tol,
+                            int32_t* invariant, int32_t* first_bad_element);
 
 /* ---- ReducedHilbertSpaceRepresentation  (Symmetry/symmetry_reduce_generic.jl:22-255) */
 /* symmetry_reduce(hsr, symops_and_amplitudes; tol).  Representatives (orbit minima whose
@@ -250,6 +258,26 @@ int ed_vector_randn_async(void* v, int64_t n, int32_t dtype, uint64_t seed, int6
 int ed_vector_scale_async(void* v, int64_t n, int32_t dtype, double a);
 /* lowest eigenvalues of the k x k symmetric tridiagonal (alpha, beta[0..k-2]) -- host helper. */
 int ed_tridiag_eigvals(const double* alpha, const double* beta, int32_t k, double* eig_out);
+
+/* ---- checkpoints (raw binary files; not in the reference, which has no persistence) ----------------------------
+ * A sector basis stores how it was generated (its rank tables are rebuilt on load), a user list its words; both are
+ * bound to the Hilbert space by a hash.  A reduced basis stores representatives, orbit sizes and stabiliser marks and is
+ * bound to the symmetry operations, characters and tolerance it was made with: loading skips the filter pass over the
+ * parent space.  Mismatching files fail with ED_ERR_ARGUMENT. */
+int ed_basis_save(ed_basis* basis, const char* path);
+int ed_basis_load(const ed_space* space, const char* path, ed_basis** out);
+int ed_rbasis_save(ed_rbasis* rbasis, const char* path);
+int ed_rbasis_load(ed_basis* parent, const ed_symmetry* sym, double tol, const char* path, ed_rbasis** out);
+/* ed_lanczos as a resumable object: create (v0 NULL = Philox vector from seed), run n_steps more steps as often as
+ * wanted, read (alpha, beta, lowest Ritz values) of all steps taken so far, save / load the full state (both Krylov
+ * vectors and the scalars).  A loaded state continues bit for bit like an uninterrupted run. */
+int ed_lanczos_state_create(ed_oprep* oprep, int32_t dtype, const void* v0, uint64_t seed, ed_lanczos_state** out);
+int ed_lanczos_state_destroy(ed_lanczos_state* state);
+int ed_lanczos_state_step(ed_lanczos_state* state, int32_t n_steps);
+int ed_lanczos_state_result(ed_lanczos_state* state, int32_t capacity, double* alpha, double* beta, double* ritz,
+                            int32_t n_ritz, int32_t* steps_done);
+int ed_lanczos_state_save(ed_lanczos_state* state, const char* path);
+int ed_lanczos_state_load(ed_oprep* oprep, const char* path, ed_lanczos_state** out);
 
 /* ---- multi-GPU: rows sharded over the GPUs of one node ------------------------------------------------
  * The reference parallelises INSIDE apply! (Threads.@threads over statically split rows,

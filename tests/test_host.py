@@ -129,3 +129,36 @@ def test_term_walk_goldens_on_host_operators(ed, golden):
         assert ed.get_column_iterator(sop, int(b)) == [tuple(e) for e in exp]
     for br, bc, v in g["element"]:
         assert abs(ed.get_element(sop, br, bc) - v) < 1e-12
+
+
+def test_isinvariant_gate_needs_no_gpu(ed):
+    """ed_operator_isinvariant (Symmetry/symmetry_apply.jl:110-135 for every element of a symmetry) against the oracle's
+    isinvariant, element by element; host only."""
+    n = 8
+    hs, pauli = ed.spin_half_system(n)
+    hs_o, pauli_o = O.spin_half_system(n)
+    L = ed.lattices
+    ring = ed.models.heisenberg_bonds(hs, L.chain_bonds(n))
+    _, ring_o = oracle_spin_chain(n)
+    symops = L.chain_translation_irrep(n, 3)
+    assert ed.isinvariant_all(hs, symops, ring) == (True, -1)
+    assert all(O.isinvariant(hs_o, O.SitePermutation(op.map), ring_o) for op, _ in symops)
+    # an open chain is not translation invariant: the first violating element is T^1
+    open_chain = ed.models.heisenberg_bonds(hs, L.chain_bonds(n, periodic=False))
+    _, open_o = oracle_spin_chain(n, [(i, i + 1) for i in range(n - 1)])
+    ok, bad = ed.isinvariant_all(hs, symops, open_chain)
+    assert not ok and bad == 1
+    assert not O.isinvariant(hs_o, O.SitePermutation(symops[1][0].map), open_o)
+    # a staggered field is invariant under even translations only
+    stag = ed.simplify(ring + sum((-1.0) ** i * pauli(i, "z") for i in range(n)))
+    ok, bad = ed.isinvariant_all(hs, symops, stag)
+    assert not ok and bad == 1
+    assert ed.isinvariant_all(hs, symops[::2], stag) == (True, -1)
+    # the same operator written with different term lists is still invariant (matrix elements, not term lists)
+    a = ed.simplify(ring + 0.5 * pauli(0, "z") * pauli(4, "z") + 0.5 * pauli(4, "z") * pauli(0, "z"))
+    inv4 = [(L.chain_translation(n, 4 * k), 1.0) for k in range(2)]
+    assert ed.isinvariant_all(hs, inv4, a) == (True, -1)
+    # global bit flip: sz sz invariant, a uniform field is not
+    flips = [(ed.SitePermutation(range(n)), 1.0), (ed.GlobalBitFlip(True), 1.0)]
+    assert ed.isinvariant_all(hs, flips, ring) == (True, -1)
+    assert ed.isinvariant_all(hs, flips, ed.simplify(ring + sum(pauli(i, "z") for i in range(n))))[0] is False

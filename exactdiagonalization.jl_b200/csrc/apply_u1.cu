@@ -1192,26 +1192,44 @@ std::shared_ptr<U1Global> u1_global_layout(const FastU1Plan* plan, int world, in
   G.rows_of_rank.assign(world, 0);
   G.off.assign(nt, 0);
   for (size_t t = 0; t < nt; ++t) { G.off[t] = G.rows_of_rank[G.owner[t]]; G.rows_of_rank[G.owner[t]] += (int64_t)plan->h_size[t]; }
+  // launch order of a rank: first its INTERIOR tiles (every tile they read is its own: they need no transfer and run
+  // while the copy engines fetch the halo), then the boundary tiles; both in the key's order
   G.launch.assign(world, {});
-  for (uint32_t t : best_order) G.launch[G.owner[t]].push_back(t);
+  std::vector<std::vector<uint32_t>> boundary(world);
+  for (uint32_t t : best_order) {
+    const int r = G.owner[t];
+    bool interior = true;
+    const int32_t* row = TG.nbr.data() + (size_t)t * TG.deg;
+    for (int d = 0; d < TG.deg && interior; ++d) interior = row[d] < 0 || G.owner[row[d]] == r;
+    (interior || world == 1 ? G.launch[r] : boundary[r]).push_back(t);
+  }
   size_t most = 1;
-  for (auto& l : G.launch) most = std::max(most, l.size());
-  n_chunks = world > 1 ? (int)std::max<size_t>(1, std::min<size_t>((size_t)n_chunks, most)) : 1;
+  for (auto& l : boundary) most = std::max(most, l.size());
+  // chunk 0 = the interior tiles; chunks 1 .. n_chunks-1 = the boundary tiles in equal row counts
+  n_chunks = world > 1 ? (int)std::max<size_t>(2, std::min<size_t>((size_t)n_chunks, most + 1)) : 1;
   G.n_chunks = n_chunks;
   G.chunk_first.assign(world, std::vector<int>(n_chunks + 1, 0));
   G.halo_tiles.assign(world, {});
   G.halo_chunk.assign(world, {});
   G.exch.assign((size_t)world * world * n_chunks, 0);
   for (int r = 0; r < world; ++r) {
-    const auto& L = G.launch[r];
+    auto& L = G.launch[r];
     auto& cf = G.chunk_first[r];
+    const int n_int = (int)L.size();
+    int64_t rows_b = 0;
+    for (uint32_t t : boundary[r]) rows_b += (int64_t)plan->h_size[t];
+    L.insert(L.end(), boundary[r].begin(), boundary[r].end());
     for (int c = 0; c <= n_chunks; ++c) cf[c] = (int)L.size();
     cf[0] = 0;
-    int c = 1;
-    int64_t acc = 0;
-    for (size_t i = 0; i < L.size() && c < n_chunks; ++i) {
-      acc += (int64_t)plan->h_size[L[i]];
-      if (acc >= G.rows_of_rank[r] / n_chunks * c) cf[c++] = (int)i + 1;
+    if (world > 1) {
+      cf[1] = n_int;
+      int c = 2;
+      int64_t acc = 0;
+      const int nb = n_chunks - 1;
+      for (size_t i = (size_t)n_int; i < L.size() && c < n_chunks; ++i) {
+        acc += (int64_t)plan->h_size[L[i]];
+        if (acc >= rows_b / nb * (c - 1)) cf[c++] = (int)i + 1;
+      }
     }
     std::vector<uint8_t> seen(nt, 0);
     for (int ch = 0; ch < n_chunks; ++ch) {

@@ -93,7 +93,7 @@ struct ed_ctx {
   bool loopback = false;        // every rank on the same device of this process: collectives emulated, no NCCL
   bool multi_process = false;   // one rank in this process; peers' buffers come through CUDA IPC
   std::vector<CtxRank> local;
-  int n_pull_streams = 2;
+  int n_pull_streams = 1;       // one: the pieces arrive in the order the launch chunks need them (measured at N=2: 4.55 vs 4.91 ms with two)
 };
 
 namespace {
@@ -829,6 +829,53 @@ int ed_apply_sharded(ed_sharded* sh, ed_dvec* y, ed_dvec* x, int32_t no_fence, d
     ED_CUDA(cudaSetDevice(R.device));
     ED_CUDA(cudaMemcpyAsync(dot_out, sh->r[0].dot.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
     ED_CUDA(cudaStreamSynchronize(R.stream));
+  }
+  ED_CATCH
+}
+
+/* One matvec taken apart (halo exchange only): ms[0] = owner-side pack, ms[1] = fence (tiny all-reduce), ms[2] = all peer
+ * copies with nothing else running, ms[3] = all kernel chunks with the halo already in place; each the max over ranks.
+ * The phases overlap in ed_apply_sharded; here they run back to back to show what bounds it. */
+int ed_sharded_profile(ed_sharded* sh, ed_dvec* y, ed_dvec* x, double* ms4) {
+  ED_TRY
+  ED_REQUIRE(sh && y && x && ms4 && y->sh == sh && x->sh == sh && y != x, ED_ERR_ARGUMENT, "bad arguments");
+  ED_REQUIRE(sh->halo, ED_ERR_UNSUPPORTED, "only the halo exchange has separate phases");
+  ed_ctx* c = sh->ctx;
+  DeviceGuard g;
+  ctx_fence(c);
+  ed_ctx_timer_record(c, 50);
+  sharded_pack(sh, x);
+  ed_ctx_timer_record(c, 51);
+  ctx_fence(c);
+  ed_ctx_timer_record(c, 52);
+  for (size_t i = 0; i < c->local.size(); ++i) {
+    CtxRank& R = c->local[i];
+    ShardRank& Q = sh->r[i];
+    ED_CUDA(cudaSetDevice(R.device));
+    ED_CUDA(cudaEventRecord(R.ev, R.stream));
+    ED_CUDA(cudaStreamWaitEvent(R.copy[0], R.ev, 0));
+    for (const U1Pull& p : Q.L.pulls)
+      ED_CUDA(cudaMemcpyAsync(Q.halo.p + (size_t)p.dst_off * sh->es, static_cast<const char*>(Q.peer_send[sh->parity][p.peer]) + (size_t)p.src_off * sh->es,
+                              (size_t)p.len * sh->es, cudaMemcpyDeviceToDevice, R.copy[0]));
+    ED_CUDA(cudaEventRecord(R.ev, R.copy[0]));
+    ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
+  }
+  ed_ctx_timer_record(c, 53);
+  for (size_t i = 0; i < c->local.size(); ++i) {
+    ShardRank& Q = sh->r[i];
+    RankScope scope(c->local[i]);
+    for (int ch = 0; ch < Q.L.n_chunks; ++ch) {
+      U1ShardLaunch A;
+      A.tile_H = Q.d_tile_H.p; A.first = Q.L.chunk_first[ch]; A.count = Q.L.chunk_first[ch + 1] - Q.L.chunk_first[ch];
+      A.dir = Q.d_dir.p; A.x_local = x->local[i]; A.x_halo = Q.halo.p; A.y_local = y->local[i];
+      A.stream_mode = 0; A.accumulate = 0; A.partials = nullptr;
+      ed_apply_u1_sharded(Q.op, sh->dtype, A);
+    }
+  }
+  ed_ctx_timer_record(c, 54);
+  for (int k = 0; k < 4; ++k) {
+    const int rc = ed_ctx_timer_elapsed(c, 50 + k, 51 + k, ms4 + k);
+    ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
   }
   ED_CATCH
 }

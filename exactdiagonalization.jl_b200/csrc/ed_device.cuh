@@ -139,6 +139,16 @@ __device__ __forceinline__ int64_t rank_word_dyn(const LookupDesc& L, uint64_t s
   }
 }
 
+// membership only ("get(basis_lookup, word, -1) > 0"): no rank needed where the index is not used
+__device__ __forceinline__ bool in_basis_dyn(const LookupDesc& L, uint64_t s) {
+  switch (L.kind) {
+    case ED_BASIS_LIST: return rank_list(L.words, L.dim, s) >= 0;
+    case ED_BASIS_FULL: return s < (uint64_t)L.dim;
+    case ED_BASIS_COMBINADIC: return !(L.n_bits < 64 && (s >> L.n_bits)) && __popcll(s) == L.n_set;
+    default: return rank_dprank(L, s) >= 0;
+  }
+}
+
 // ------------------------------------------------------------------ group action
 // symmetry_apply (src/Symmetry/symmetry_apply.jl:82-92, bitflipsymmetry.jl:23-35) as byte-chunk
 // LUTs: image = OR_c lut[g][c][byte_c]; a GlobalBitFlip is folded into the tables.

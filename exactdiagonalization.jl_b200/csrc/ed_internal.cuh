@@ -282,7 +282,11 @@ struct CsrCache {
   bool val_complex = false;
   DevBuf<int64_t> rowptr;   // 0-based, row_hi-row_lo+1 entries (released when the matrix is column-blocked)
   DevBuf<int32_t> col;      // 0-based
-  DevBuf<double> val;       // nnz doubles or nnz (re,im) pairs
+  DevBuf<double> val;       // nnz doubles or nnz (re,im) pairs (released when the values are dictionary coded)
+  bool coded = false;       // real values stored as 16-bit codes into `lut` (sparse.cu: csr_code_values)
+  int n_values = 0;
+  DevBuf<uint16_t> code;
+  DevBuf<double> lut;
   // column blocking (x larger than the L2): the entries regrouped block-major -- block b holds, row by row, the entries
   // whose column lies in [b * block_cols, (b + 1) * block_cols) -- so that one pass per block gathers x from an L2-sized window
   int n_blocks = 1;

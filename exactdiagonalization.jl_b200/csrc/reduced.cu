@@ -52,7 +52,7 @@ k6_apply_reduced(LookupDesc L, SymDesc S, RLookupDesc R, int64_t row_lo, int64_t
         j = r;
         a2 = a_self;  // already conjugated when conj_side
       } else {
-        if (rank_word_dyn(L, b2) < 0) continue;
+        if (!in_basis_dyn(L, b2)) continue;
         j = reduced_map_word(S, R, b2, &a2);
         if (j < 0) continue;
         if (conj_side) a2 = cconj(a2);

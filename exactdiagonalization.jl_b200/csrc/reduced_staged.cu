@@ -28,14 +28,31 @@ struct K6Terms {
   int amp_complex;
 };
 
+// the term table staged in shared memory (broadcast LDS instead of uniform global loads in the per-row term walks)
+struct K6TermsS {
+  const uint64_t* mask; const uint64_t* match; const uint64_t* target;
+};
+__device__ __forceinline__ K6TermsS k6_stage_terms(const K6Terms& T, unsigned char* smem) {
+  uint64_t* m = reinterpret_cast<uint64_t*>(smem);
+  for (int t = threadIdx.x; t < T.n_terms; t += blockDim.x) {
+    m[t] = __ldg(T.mask + t);
+    m[T.n_terms + t] = __ldg(T.match + t);
+    m[2 * T.n_terms + t] = __ldg(T.target + t);
+  }
+  __syncthreads();
+  return K6TermsS{m, m + T.n_terms, m + 2 * T.n_terms};
+}
+
 __global__ void __launch_bounds__(256)
 k6a_count(K6Terms T, const uint64_t* __restrict__ rwords, int64_t row0, int64_t n, int64_t* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char k6_smem[];
+  const K6TermsS TS = k6_stage_terms(T, k6_smem);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t b = __ldg(rwords + row0 + i);
     int c = 0;
     for (int t = 0; t < T.n_terms; ++t) {
-      const uint64_t m = __ldg(T.mask + t);
-      if ((b & m) == __ldg(T.match + t) && ((b & ~m) | __ldg(T.target + t)) != b) ++c;
+      const uint64_t m = TS.mask[t];
+      if ((b & m) == TS.match[t] && ((b & ~m) | TS.target[t]) != b) ++c;
     }
     counts[i] = c;
   }
@@ -44,13 +61,15 @@ k6a_count(K6Terms T, const uint64_t* __restrict__ rwords, int64_t row0, int64_t 
 __global__ void __launch_bounds__(256)
 k6a_emit(K6Terms T, const uint64_t* __restrict__ rwords, int64_t row0, int64_t n, const int64_t* __restrict__ offs,
          uint64_t* __restrict__ hit_words) {
+  extern __shared__ __align__(16) unsigned char k6_smem[];
+  const K6TermsS TS = k6_stage_terms(T, k6_smem);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t b = __ldg(rwords + row0 + i);
     int64_t at = offs[i];
     for (int t = 0; t < T.n_terms; ++t) {
-      const uint64_t m = __ldg(T.mask + t);
-      if ((b & m) != __ldg(T.match + t)) continue;
-      const uint64_t b2 = (b & ~m) | __ldg(T.target + t);
+      const uint64_t m = TS.mask[t];
+      if ((b & m) != TS.match[t]) continue;
+      const uint64_t b2 = (b & ~m) | TS.target[t];
       if (b2 != b) hit_words[at++] = b2;
     }
   }
@@ -220,11 +239,142 @@ k6b_canonicalize_tr(int n_cos, int n1_rt, int n2_rt, int n_bits_rt, const uint64
   }
 }
 
+// B (necklace): the same minimum / element selection again, but the n1 x n2 translations of a coset image are not swept
+// at all.  The minimum over Tx^a Ty^b of a word has, as its most significant row, the smallest ROTATION of any of the
+// word's rows: a 2^n1-entry table gives for every row value its minimal rotation and the set of shifts a that reach it.
+// Per coset: one table look-up per row, the row minimum m, and -- only when m does not exceed the top row of the best word
+// so far -- a full comparison for the few (row, shift) pairs that reach m (usually one).  Every element attaining the
+// global minimum is among those candidates (it must minimise the top row inside its coset), so (best, besti) come out
+// exactly as in the full sweep: ~45 instead of ~245 instructions per (word, coset).
+template <int NCH, int N1, int N2>
+__global__ void __launch_bounds__(256)
+k6b_canonicalize_nk(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict__ lut6c, const int32_t* __restrict__ tinv,
+                    int64_t n_words, uint64_t* __restrict__ words, uint16_t* __restrict__ garg) {
+  constexpr int W = 2;          // words per thread
+  constexpr int CB = 4;         // cosets staged per barrier
+  constexpr bool FIXED = N1 > 0;
+  const int n1 = FIXED ? N1 : n1_rt, n2 = FIXED ? N2 : n2_rt, n_bits = n1 * n2;
+  extern __shared__ __align__(16) unsigned char k6_smem[];
+  uint64_t* s_lut = reinterpret_cast<uint64_t*>(k6_smem);                   // [2][CB * NCH * 64]
+  int32_t* s_inv = reinterpret_cast<int32_t*>(s_lut + 2 * CB * NCH * 64);   // [2][CB * n1 * n2]
+  uint64_t* s_mlo = reinterpret_cast<uint64_t*>(s_inv + 2 * CB * n1 * n2 + ((2 * CB * n1 * n2) & 1));   // [8] columns x < a of every row
+  uint16_t* s_row = reinterpret_cast<uint16_t*>(s_mlo + 8);                 // [2^n1] (minimal rotation << 8) | shifts reaching it
+  const int nt = n1 * n2;
+  const int tid = threadIdx.x;
+  const uint64_t full = n_bits >= 64 ? ~0ull : ((1ull << n_bits) - 1ull);
+  const uint32_t rmask = (1u << n1) - 1u;
+  for (int v = tid; v < (1 << n1); v += 256) {
+    uint32_t best = (uint32_t)v, arg = 1u, r = (uint32_t)v;
+    for (int a = 1; a < n1; ++a) {
+      r = ((r << 1) | (r >> (n1 - 1))) & rmask;                // rotate left by one: Tx on one row
+      if (r < best) { best = r; arg = 1u << a; }
+      else if (r == best) arg |= 1u << a;
+    }
+    s_row[v] = (uint16_t)((best << 8) | arg);
+  }
+  if (tid < 8) {
+    uint64_t m = 0;
+    for (int y = 0; y < n2; ++y) m |= (uint64_t)((1u << tid) - 1u) << (n1 * y);
+    s_mlo[tid] = tid <= n1 ? (m & full) : 0ull;
+  }
+  const int64_t base = (int64_t)blockIdx.x * (256 * W);
+  uint64_t w[W], best[W];
+  int besti[W];
+  uint32_t off[W][NCH];
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int64_t i = base + tid + k * 256;
+    w[k] = i < n_words ? words[i] : 0ull;
+    best[k] = w[k];
+    besti[k] = 0;   // identity (element 0, its own inverse)
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) off[k][c] = (uint32_t)((w[k] >> (6 * c)) & 63ull) + c * 64;
+  }
+  const int n_batches = (n_cos + CB - 1) / CB;
+  auto stage = [&](int batch, int buf) {
+    const int j0 = batch * CB;
+    const int nj = min(CB, n_cos - j0);
+    const uint64_t* src = lut6c + (size_t)j0 * NCH * 64;
+    uint64_t* dst = s_lut + (size_t)buf * CB * NCH * 64;
+    for (int i = tid; i < nj * NCH * 64; i += 256) dst[i] = __ldg(src + i);
+    int32_t* di = s_inv + (size_t)buf * CB * nt;
+    for (int i = tid; i < nj * nt; i += 256) di[i] = __ldg(tinv + (size_t)j0 * nt + i);
+  };
+  stage(0, 0);
+  __syncthreads();
+  const int top_shift = n_bits - n1;
+  for (int batch = 0; batch < n_batches; ++batch) {
+    const int buf = batch & 1;
+    if (batch + 1 < n_batches) stage(batch + 1, buf ^ 1);
+    const int nj = min(CB, n_cos - batch * CB);
+    for (int ji = 0; ji < nj; ++ji) {
+      const uint64_t* L = s_lut + ((size_t)buf * CB + ji) * NCH * 64;
+      const int32_t* inv_tab = s_inv + ((size_t)buf * CB + ji) * nt;
+      uint64_t im[W];
+      uint32_t m[W];
+      bool cand = false;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) v |= L[off[k][c]];
+        im[k] = v;
+        uint32_t mm = 0xFFu;
+#pragma unroll(FIXED ? N2 : 1)
+        for (int y = 0; y < n2; ++y) mm = min(mm, (uint32_t)s_row[(uint32_t)(v >> (n1 * y)) & rmask] >> 8);
+        m[k] = mm;
+        cand |= mm <= (uint32_t)(best[k] >> top_shift);
+      }
+      if (__any_sync(0xffffffffu, cand)) {            // warp-uniform branch: most cosets cannot beat the best word so far
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+          if (m[k] > (uint32_t)(best[k] >> top_shift)) continue;
+          for (int y = 0; y < n2; ++y) {
+            const uint32_t t = s_row[(uint32_t)(im[k] >> (n1 * y)) & rmask];
+            if ((t >> 8) != m[k]) continue;
+            const int b = n2 - 1 - y;                  // Ty^b brings row y to the top
+            const uint64_t ub = b ? (((im[k] << (n1 * b)) | (im[k] >> (n_bits - n1 * b))) & full) : im[k];
+            uint32_t shifts = t & 0xFFu;
+            while (shifts) {
+              const int a = __ffs(shifts) - 1;
+              shifts &= shifts - 1u;
+              const uint64_t mlo = s_mlo[a];
+              const uint64_t u = a ? (((ub << a) & full & ~mlo) | ((ub >> (n1 - a)) & mlo)) : ub;     // Tx^a
+              const int inv = inv_tab[b * n1 + a];
+              if (u < best[k]) { best[k] = u; besti[k] = inv; }
+              else if (u == best[k] && inv > besti[k]) besti[k] = inv;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < W; ++k) {
+    const int64_t i = base + tid + k * 256;
+    if (i < n_words) { words[i] = best[k]; garg[i] = (uint16_t)besti[k]; }
+  }
+}
+
+// B': representative index and orbit size of every canonical word, word-parallel (independent searches: the memory
+// latency of the bucketed binary search is hidden by parallelism instead of sitting inside the per-row combine loop)
+__global__ void __launch_bounds__(256)
+k6b_lookup(RLookupDesc R, int64_t n_words, const uint64_t* __restrict__ words, int32_t* __restrict__ hit_j, uint16_t* __restrict__ hit_orbit) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_words; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = rank_reduced(R, __ldg(words + i));
+    hit_j[i] = (int32_t)j;
+    hit_orbit[i] = j >= 0 ? __ldg(R.orbit_size + j) : (uint16_t)1;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int64_t n, int64_t out_row0,
-            const int64_t* __restrict__ offs, const uint64_t* __restrict__ min_words, const uint16_t* __restrict__ garg,
-            int conj_side, const c128* __restrict__ x, c128* __restrict__ out, int accumulate,
+            const int64_t* __restrict__ offs, const int32_t* __restrict__ hit_j, const uint16_t* __restrict__ hit_orbit,
+            const uint16_t* __restrict__ garg, int conj_side, const c128* __restrict__ x, c128* __restrict__ out, int accumulate,
             double* __restrict__ dot_partials, int partial_slot0) {
+  extern __shared__ __align__(16) unsigned char k6_smem[];
+  const K6TermsS TS = k6_stage_terms(T, k6_smem);
   double dre = 0.0, dim_ = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = row0 + i;
@@ -235,9 +385,9 @@ k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int
     c128 acc = accumulate ? out[out_row0 + i] : make_c128(0.0, 0.0);
     int64_t at = offs[i];
     for (int t = 0; t < T.n_terms; ++t) {
-      const uint64_t m = __ldg(T.mask + t);
-      if ((b & m) != __ldg(T.match + t)) continue;
-      const uint64_t b2 = (b & ~m) | __ldg(T.target + t);
+      const uint64_t m = TS.mask[t];
+      if ((b & m) != TS.match[t]) continue;
+      const uint64_t b2 = (b & ~m) | TS.target[t];
       const c128 a = T.amp_complex ? make_c128(__ldg(T.amp + 2 * t), __ldg(T.amp + 2 * t + 1)) : make_c128(__ldg(T.amp + t), 0.0);
       int64_t j;
       c128 a2;
@@ -245,13 +395,13 @@ k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int
         j = r;
         a2 = a_self;
       } else {
-        const uint64_t mw = min_words[at];
+        j = hit_j[at];
         const int gi = garg[at];
+        const double norm2 = (double)hit_orbit[at];
         ++at;
-        if (rank_word_dyn(L, b2) < 0) continue;                 // not in the parent basis
-        j = rank_reduced(R, mw);
         if (j < 0) continue;                                     // orbit not in this irrep
-        const double inv_norm = 1.0 / sqrt((double)__ldg(R.orbit_size + j));
+        if (!in_basis_dyn(L, b2)) continue;                     // not in the parent basis
+        const double inv_norm = 1.0 / sqrt(norm2);
         a2 = make_c128(__ldg(S.chi + 2 * gi) * inv_norm, -__ldg(S.chi + 2 * gi + 1) * inv_norm);
         if (conj_side) a2 = cconj(a2);
       }
@@ -281,7 +431,7 @@ k6c_combine(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int
 // instead of one row-per-thread orbit search per hit.  Same arithmetic as k6c_combine / walk_line.
 __global__ void __launch_bounds__(128)
 k6c_fill_raw(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, int64_t n, const int64_t* __restrict__ hit_offs,
-             const uint64_t* __restrict__ min_words, const uint16_t* __restrict__ garg, int conj_side,
+             const int32_t* __restrict__ hit_j, const uint16_t* __restrict__ hit_orbit, const uint16_t* __restrict__ garg, int conj_side,
              const int64_t* __restrict__ raw_offs, int64_t* __restrict__ raw_row, c128* __restrict__ raw_val) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = row0 + i;
@@ -302,13 +452,14 @@ k6c_fill_raw(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, in
         j = r;
         v = cmul(cmul(a, a_self), inv_self);
       } else {
-        const uint64_t mw = min_words[at];
+        const int64_t jj = hit_j[at];
         const int gi = garg[at];
+        const double norm2 = (double)hit_orbit[at];
         ++at;
-        if (rank_word_dyn(L, b2) >= 0) {
-          j = rank_reduced(R, mw);
+        if (in_basis_dyn(L, b2)) {
+          j = jj;
           if (j >= 0) {
-            const double inv_norm = 1.0 / sqrt((double)__ldg(R.orbit_size + j));
+            const double inv_norm = 1.0 / sqrt(norm2);
             c128 a2 = make_c128(__ldg(S.chi + 2 * gi) * inv_norm, -__ldg(S.chi + 2 * gi + 1) * inv_norm);
             if (conj_side) a2 = cconj(a2);
             v = cmul(cmul(a, a2), inv_self);
@@ -325,7 +476,8 @@ k6c_fill_raw(K6Terms T, LookupDesc L, SymDesc S, RLookupDesc R, int64_t row0, in
 struct K6Scratch {
   DevBuf<int64_t> counts, offs;
   DevBuf<uint64_t> words;
-  DevBuf<uint16_t> garg;
+  DevBuf<uint16_t> garg, horb;
+  DevBuf<int32_t> hitj;
   DevBuf<unsigned char> tmp;
   DevBuf<double> partials;
 };
@@ -345,7 +497,8 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
   if (sc.counts.n < (size_t)nb + 1) { sc.counts.alloc((size_t)nb + 1); sc.offs.alloc((size_t)nb + 1); }
   ED_CUDA(cudaMemsetAsync(sc.counts.p + nb, 0, sizeof(int64_t), ed_stream()));
   const int grid_a = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 255) / 256, (int64_t)sm * 16));
-  ED_LAUNCH(k6a_count, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.counts.p);
+  const size_t smem_t = (size_t)3 * T.n_terms * sizeof(uint64_t);
+  ED_LAUNCH(k6a_count, grid_a, 256, smem_t, T, rb->words.p, row0, nb, sc.counts.p);
   size_t bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
   if (sc.tmp.n < bytes) sc.tmp.alloc(bytes);
@@ -357,16 +510,35 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
   if (sc.words.n < (size_t)std::max<int64_t>(n_hits, 1)) {
     sc.words.alloc((size_t)std::max<int64_t>(n_hits, 1));
     sc.garg.alloc((size_t)std::max<int64_t>(n_hits, 1));
+    sc.horb.alloc((size_t)std::max<int64_t>(n_hits, 1));
+    sc.hitj.alloc((size_t)std::max<int64_t>(n_hits, 1));
   }
   if (n_hits > 0) {
-    ED_LAUNCH(k6a_emit, grid_a, 256, 0, T, rb->words.p, row0, nb, sc.offs.p, sc.words.p);
+    ED_LAUNCH(k6a_emit, grid_a, 256, smem_t, T, rb->words.p, row0, nb, sc.offs.p, sc.words.p);
     if (ev_mid) ED_CUDA(cudaEventRecord(ev_mid, ed_stream()));
     const int grid_b = (int)((n_hits + 1023) / 1024);
     const int nch = rb->symdev.n_chunks6;
     const uint64_t* lut6 = rb->symdev.lut6.p;
     const int32_t* inv = rb->symdev.inverse.p;
     const SymDev& sd = rb->symdev;
-    if (sd.tr_on && nch <= 8) {
+    static const bool no_necklace = getenv("EDCUDA_K6_NONECKLACE") != nullptr;
+    if (sd.tr_on && nch <= 8 && sd.tr_n1 <= 8 && sd.tr_n1 >= 2 && parent->space.bits == sd.tr_n1 * sd.tr_n2 && !no_necklace) {
+      const int nt_ = sd.tr_n1 * sd.tr_n2;
+      const int grid_n = (int)((n_hits + 511) / 512);
+#define ED_K6NK(NCH_, N1_, N2_)                                                                                              \
+      do {                                                                                                                   \
+        const size_t smem_n = (size_t)2 * 4 * NCH_ * 64 * 8 + (size_t)(2 * 4 * nt_ + ((2 * 4 * nt_) & 1)) * 4 + 8 * 8 + ((size_t)2 << sd.tr_n1); \
+        ED_LAUNCH((k6b_canonicalize_nk<NCH_, N1_, N2_>), grid_n, 256, smem_n, sd.tr_ncos, sd.tr_n1, sd.tr_n2, sd.tr_lut6.p, \
+                  sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);                                                               \
+      } while (0)
+      if (sd.tr_n1 == 6 && sd.tr_n2 == 6 && nch == 6) ED_K6NK(6, 6, 6);
+      else if (sd.tr_n1 == 4 && sd.tr_n2 == 4 && nch <= 4) ED_K6NK(4, 4, 4);
+      else if (nch <= 4) ED_K6NK(4, 0, 0);
+      else if (nch <= 6) ED_K6NK(6, 0, 0);
+      else ED_K6NK(8, 0, 0);
+#undef ED_K6NK
+    }
+    else if (sd.tr_on && nch <= 8) {
       const size_t smem = (size_t)2 * 4 * nch * 64 * 8 + (size_t)2 * 4 * sd.tr_n1 * sd.tr_n2 * 4;
       const int nb_ = parent->space.bits;
 #define ED_K6TR(NCH_, N1_, N2_)                                                                                               \
@@ -384,6 +556,11 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
     else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
     else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
     else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
+    RLookupDesc R;
+    R.words = rb->words.p; R.orbit_size = rb->orbit_size.p; R.last_stab = rb->last_stab.p;
+    R.bucket_start = rb->bucket_start.p; R.bucket_shift = rb->bucket_shift; R.n_buckets = rb->n_buckets; R.dim = rb->dim;
+    const int grid_l = (int)std::max<int64_t>(1, std::min<int64_t>((n_hits + 255) / 256, (int64_t)sm * 32));
+    ED_LAUNCH(k6b_lookup, grid_l, 256, 0, R, n_hits, sc.words.p, sc.hitj.p, sc.horb.p);
   }
   return n_hits;
 }
@@ -392,7 +569,8 @@ bool ed_apply_reduced_staged_supported(ed_oprep* o) {
   const ed_rbasis* rb = o->rbasis;
   const char* e = getenv("EDCUDA_K6_MIN_ROWS");   // rows below which the simple row-per-thread kernel is used
   const int64_t min_rows = e ? atoll(e) : 2048;
-  return rb && rb->symdev.lut6.n > 0 && rb->symdev.n_chunks6 <= 11 && (o->row_hi - o->row_lo) >= min_rows;
+  return rb && rb->symdev.lut6.n > 0 && rb->symdev.n_chunks6 <= 11 && (o->row_hi - o->row_lo) >= min_rows &&
+         o->op.n_terms <= 1900;        // the term table is staged in (static-limit) shared memory: 24 B per term
 }
 
 void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, int accumulate, double* alpha_dot) {
@@ -429,7 +607,7 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
     const int64_t n_hits = k6_stage_batch(o, T, row0, nb, sc, timing ? ev[1] : nullptr);
     if (timing) ED_CUDA(cudaEventRecord(ev[2], ed_stream()));
     const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 127) / 128, (int64_t)grid_c_max));
-    ED_LAUNCH(k6c_combine, grid_c, 128, 0, T, L, S, R, row0, nb, b0, sc.offs.p, sc.words.p, sc.garg.p,
+    ED_LAUNCH(k6c_combine, grid_c, 128, (size_t)3 * T.n_terms * sizeof(uint64_t), T, L, S, R, row0, nb, b0, sc.offs.p, sc.hitj.p, sc.horb.p, sc.garg.p,
               side == ED_SIDE_RIGHT ? 1 : 0, reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate,
               alpha_dot ? sc.partials.p : nullptr, slots_used);
     slots_used += grid_c;
@@ -449,7 +627,7 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
 // raw entries of lines [line0, line0 + n) of a reduced representation for the sparse assembly (sparse.cu)
 bool ed_reduced_fill_raw_staged(ed_oprep* o, int side, int64_t line0, int64_t n, const int64_t* raw_offs, int64_t* raw_row, void* raw_val) {
   const ed_rbasis* rbc = o->rbasis;
-  if (!rbc || rbc->symdev.lut6.n == 0 || rbc->symdev.n_chunks6 > 11 || getenv("EDCUDA_K6_SIMPLE")) return false;
+  if (!rbc || rbc->symdev.lut6.n == 0 || rbc->symdev.n_chunks6 > 11 || o->op.n_terms > 1900 || getenv("EDCUDA_K6_SIMPLE")) return false;
   ed_upload_terms(o);
   ed_rbasis* rb = o->rbasis;
   ed_basis* parent = rb->parent;
@@ -464,7 +642,7 @@ bool ed_reduced_fill_raw_staged(ed_oprep* o, int side, int64_t line0, int64_t n,
   K6Scratch& sc = scratch();
   k6_stage_batch(o, T, line0, n, sc, nullptr);
   const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)ed_sm_count() * 16));
-  ED_LAUNCH(k6c_fill_raw, grid_c, 128, 0, T, L, S, R, line0, n, sc.offs.p, sc.words.p, sc.garg.p, side == ED_SIDE_RIGHT ? 1 : 0,
+  ED_LAUNCH(k6c_fill_raw, grid_c, 128, 0, T, L, S, R, line0, n, sc.offs.p, sc.hitj.p, sc.horb.p, sc.garg.p, side == ED_SIDE_RIGHT ? 1 : 0,
             raw_offs, raw_row, reinterpret_cast<c128*>(raw_val));
   return true;
 }

@@ -217,8 +217,10 @@ __global__ void __launch_bounds__(256) k_take_real(int64_t nnz, const double* __
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) rval[i] = cval[2 * i];
 }
 
-__device__ __forceinline__ c128 ld_mat(const c128* v, int64_t i) { return ldg_c128(v + i); }
-__device__ __forceinline__ double ld_mat(const double* v, int64_t i) { return __ldg(v + i); }
+// matrix values: ComplexF64, Float64, or a 16-bit code into a dictionary of the distinct values (CsrCache::coded)
+__device__ __forceinline__ c128 ld_mat(const c128* v, int64_t i, const double*) { return ldg_c128(v + i); }
+__device__ __forceinline__ double ld_mat(const double* v, int64_t i, const double*) { return __ldg(v + i); }
+__device__ __forceinline__ double ld_mat(const uint16_t* v, int64_t i, const double* lut) { return __ldg(lut + __ldg(v + i)); }
 __device__ __forceinline__ void mat_fma(double& acc, double a, double x) { acc = fma(a, x, acc); }
 __device__ __forceinline__ void mat_fma(c128& acc, double a, c128 x) { acc.re = fma(a, x.re, acc.re); acc.im = fma(a, x.im, acc.im); }
 __device__ __forceinline__ void mat_fma(c128& acc, c128 a, c128 x) { fma_acc(acc, a, x); }
@@ -227,7 +229,7 @@ __device__ __forceinline__ void mat_fma(c128& acc, c128 a, c128 x) { fma_acc(acc
 template <typename VecT, typename ValT>
 __global__ void __launch_bounds__(256)
 k_spmv_csr(int64_t n_rows, int64_t row_lo, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-           const ValT* __restrict__ val, const VecT* __restrict__ x, VecT* __restrict__ y, int accumulate,
+           const ValT* __restrict__ val, const double* __restrict__ lut, const VecT* __restrict__ x, VecT* __restrict__ y, int accumulate,
            double* __restrict__ dot_partials) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -236,7 +238,7 @@ k_spmv_csr(int64_t n_rows, int64_t row_lo, const int64_t* __restrict__ rowptr, c
   for (int64_t r = warp0; r < n_rows; r += nwarps) {
     const int64_t b = __ldg(rowptr + r), e = __ldg(rowptr + r + 1);
     VecT acc = vzero((VecT*)nullptr);
-    for (int64_t p = b + lane; p < e; p += 32) mat_fma(acc, ld_mat(val, p), ldg_val(x + __ldg(col + p)));
+    for (int64_t p = b + lane; p < e; p += 32) mat_fma(acc, ld_mat(val, p, lut), ldg_val(x + __ldg(col + p)));
     if (sizeof(VecT) == 16) {
       c128* a = reinterpret_cast<c128*>(&acc);
       a->re = warp_sum(a->re);
@@ -322,17 +324,56 @@ k_blk_fill(int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __
   }
 }
 
-__device__ __forceinline__ double ld_mat_cs(const double* v, int64_t i) { return __ldcs(v + i); }
-__device__ __forceinline__ c128 ld_mat_cs(const c128* v, int64_t i) {
+__device__ __forceinline__ double ld_mat_cs(const double* v, int64_t i, const double*) { return __ldcs(v + i); }
+__device__ __forceinline__ c128 ld_mat_cs(const c128* v, int64_t i, const double*) {
   const double2 t = __ldcs(reinterpret_cast<const double2*>(v) + i);
   return make_c128(t.x, t.y);
+}
+__device__ __forceinline__ double ld_mat_cs(const uint16_t* v, int64_t i, const double* lut) { return __ldg(lut + __ldcs(v + i)); }
+
+// ---- value dictionary ------------------------------------------------------------------------------------------------
+// The entries of a (reduced) Hamiltonian take few distinct values -- a * sqrt(N_r / N_r') * chi with a handful of
+// amplitudes, orbit sizes and characters -- so real-valued cached matrices store a 16-bit code per entry and a small
+// table instead of 8-byte doubles: 6 instead of 12 bytes per entry to stream.  Values are keyed by bit pattern (exact);
+// more than 65,535 distinct values leave the matrix uncoded.
+#define ED_DICT_SLOTS (1u << 18)
+#define ED_DICT_EMPTY 0x7FF8DEADBEEF0001ull
+__device__ __forceinline__ uint32_t dict_hash(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33;
+  return (uint32_t)k & (ED_DICT_SLOTS - 1u);
+}
+__global__ void __launch_bounds__(256) k_dict_insert(int64_t nnz, const double* __restrict__ val, unsigned long long* __restrict__ table, int* __restrict__ count) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(val[i]);
+    uint32_t slot = dict_hash(key);
+    for (int probe = 0; probe < (int)ED_DICT_SLOTS; ++probe) {
+      unsigned long long cur = table[slot];
+      if (cur == key) break;
+      if (cur == ED_DICT_EMPTY) {
+        if (*count > 70000) return;                        // hopeless: stop filling the table
+        cur = atomicCAS(table + slot, (unsigned long long)ED_DICT_EMPTY, key);
+        if (cur == ED_DICT_EMPTY) { atomicAdd(count, 1); break; }
+        if (cur == key) break;
+      }
+      slot = (slot + 1u) & (ED_DICT_SLOTS - 1u);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_dict_encode(int64_t nnz, const double* __restrict__ val, const unsigned long long* __restrict__ table,
+                                                     const uint16_t* __restrict__ slot_code, uint16_t* __restrict__ code) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long key = (unsigned long long)__double_as_longlong(__ldcs(val + i));
+    uint32_t slot = dict_hash(key);
+    while (__ldg(table + slot) != key) slot = (slot + 1u) & (ED_DICT_SLOTS - 1u);
+    code[i] = __ldg(slot_code + slot);
+  }
 }
 
 // mode 0: y = partial (first block of mul!), 1: y += partial.  dot_partials only on the last block (y is final there).
 template <typename VecT, typename ValT, int LANES>
 __global__ void __launch_bounds__(256)
 k_spmv_csr_blk(int64_t n_rows, int64_t row_lo, const uint32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-               const ValT* __restrict__ val, const VecT* __restrict__ x, VecT* __restrict__ y, int mode,
+               const ValT* __restrict__ val, const double* __restrict__ lut, const VecT* __restrict__ x, VecT* __restrict__ y, int mode,
                double* __restrict__ dot_partials) {
   const int sub = threadIdx.x & (LANES - 1);
   const int64_t grp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / LANES;
@@ -356,9 +397,9 @@ k_spmv_csr_blk(int64_t n_rows, int64_t row_lo, const uint32_t* __restrict__ rowp
 #pragma unroll
       for (int u = 0; u < 4; ++u) xv[u] = ldg_val(x + j[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) mat_fma(acc, ld_mat_cs(val, p + u * LANES), xv[u]);
+      for (int u = 0; u < 4; ++u) mat_fma(acc, ld_mat_cs(val, p + u * LANES, lut), xv[u]);
     }
-    for (; p < e; p += LANES) mat_fma(acc, ld_mat_cs(val, p), ldg_val(x + __ldcs(col + p)));
+    for (; p < e; p += LANES) mat_fma(acc, ld_mat_cs(val, p, lut), ldg_val(x + __ldcs(col + p)));
     if (LANES > 1) {
       if (sizeof(VecT) == 16) {
         c128* a = reinterpret_cast<c128*>(&acc);
@@ -456,6 +497,46 @@ static void csr_block_columns(ed_oprep* o, CsrCache* c) {
 
 void ed_reduce_pairs(const double* partials, int n, double* out2);  // apply.cu
 
+// replace the Float64 values of a cached matrix by 16-bit codes + dictionary when it has at most 65,535 distinct values
+static void csr_code_values(CsrCache* c) {
+  const int64_t nnz = c->nnz;
+  DevBuf<unsigned long long> table((size_t)ED_DICT_SLOTS);
+  DevBuf<int> count(1);
+  std::vector<unsigned long long> h_table((size_t)ED_DICT_SLOTS, ED_DICT_EMPTY);
+  table.upload(h_table);
+  ED_CUDA(cudaMemsetAsync(count.p, 0, sizeof(int), ed_stream()));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nnz + 255) / 256, (int64_t)ed_sm_count() * 16));
+  ED_LAUNCH(k_dict_insert, grid, 256, 0, nnz, c->val.p, table.p, count.p);
+  int n_distinct = 0;
+  count.download(&n_distinct, 1);
+  if (n_distinct <= 0 || n_distinct > 65535) return;
+  table.download(h_table.data(), h_table.size());
+  std::vector<std::pair<double, uint32_t>> vals;     // (value, slot)
+  for (uint32_t s = 0; s < ED_DICT_SLOTS; ++s)
+    if (h_table[s] != ED_DICT_EMPTY) {
+      double v;
+      memcpy(&v, &h_table[s], sizeof(double));
+      vals.push_back({v, s});
+    }
+  if ((int)vals.size() != n_distinct) return;
+  std::sort(vals.begin(), vals.end(), [](const std::pair<double, uint32_t>& a, const std::pair<double, uint32_t>& b) {
+    if (a.first != b.first) return a.first < b.first;
+    return a.second < b.second;
+  });
+  std::vector<double> lut(vals.size());
+  std::vector<uint16_t> slot_code((size_t)ED_DICT_SLOTS, 0);
+  for (size_t k = 0; k < vals.size(); ++k) { lut[k] = vals[k].first; slot_code[vals[k].second] = (uint16_t)k; }
+  DevBuf<uint16_t> d_slot_code;
+  d_slot_code.upload(slot_code);
+  c->lut.upload(lut);
+  c->code.alloc((size_t)nnz);
+  ED_LAUNCH(k_dict_encode, grid, 256, 0, nnz, c->val.p, table.p, d_slot_code.p, c->code.p);
+  ED_CUDA(cudaStreamSynchronize(ed_stream()));
+  c->val.release();
+  c->coded = true;
+  c->n_values = (int)vals.size();
+}
+
 void ed_csr_cache_build(ed_oprep* o, int side) {
   auto cache = std::make_shared<CsrCache>();
   cache->side = side;
@@ -488,6 +569,7 @@ void ed_csr_cache_build(ed_oprep* o, int side) {
     cache->val = std::move(val);
   }
   if (!getenv("EDCUDA_CSR_NOBLOCK")) csr_block_columns(o, cache.get());
+  if (!cache->val_complex && nnz > 0 && !getenv("EDCUDA_CSR_NOCODE")) csr_code_values(cache.get());
   o->csr[side] = cache;
 }
 
@@ -521,15 +603,21 @@ void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, in
       double* dp = (b == c->n_blocks - 1) ? partials : nullptr;
 #define ED_BLK_LAUNCH(L)                                                                                                        \
       do {                                                                                                                      \
-        if (dtype == ED_F64)                                                                                                    \
+        if (c->coded && dtype == ED_F64)                                                                                        \
+          ED_LAUNCH((k_spmv_csr_blk<double, uint16_t, L>), grid_b, 256, 0, n, c->row_lo, rp, cb, c->code.p + c->blk_base[b],    \
+                    c->lut.p, reinterpret_cast<const double*>(x), reinterpret_cast<double*>(out), mode, dp);                    \
+        else if (c->coded)                                                                                                      \
+          ED_LAUNCH((k_spmv_csr_blk<c128, uint16_t, L>), grid_b, 256, 0, n, c->row_lo, rp, cb, c->code.p + c->blk_base[b],      \
+                    c->lut.p, reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), mode, dp);                        \
+        else if (dtype == ED_F64)                                                                                               \
           ED_LAUNCH((k_spmv_csr_blk<double, double, L>), grid_b, 256, 0, n, c->row_lo, rp, cb, c->val.p + c->blk_base[b],       \
-                    reinterpret_cast<const double*>(x), reinterpret_cast<double*>(out), mode, dp);                              \
+                    nullptr, reinterpret_cast<const double*>(x), reinterpret_cast<double*>(out), mode, dp);                     \
         else if (!c->val_complex)                                                                                               \
           ED_LAUNCH((k_spmv_csr_blk<c128, double, L>), grid_b, 256, 0, n, c->row_lo, rp, cb, c->val.p + c->blk_base[b],         \
-                    reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), mode, dp);                                  \
+                    nullptr, reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), mode, dp);                         \
         else                                                                                                                    \
           ED_LAUNCH((k_spmv_csr_blk<c128, c128, L>), grid_b, 256, 0, n, c->row_lo, rp, cb,                                      \
-                    reinterpret_cast<const c128*>(c->val.p) + c->blk_base[b], reinterpret_cast<const c128*>(x),                 \
+                    reinterpret_cast<const c128*>(c->val.p) + c->blk_base[b], nullptr, reinterpret_cast<const c128*>(x),        \
                     reinterpret_cast<c128*>(out), mode, dp);                                                                    \
       } while (0)
       if (lanes == 1) ED_BLK_LAUNCH(1);
@@ -541,14 +629,20 @@ void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, in
     if (alpha_dot) ed_reduce_pairs(partials, grid_b, alpha_dot);
     return;
   }
-  if (dtype == ED_F64)
-    ED_LAUNCH((k_spmv_csr<double, double>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->val.p,
+  if (c->coded && dtype == ED_F64)
+    ED_LAUNCH((k_spmv_csr<double, uint16_t>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->code.p, c->lut.p,
+              reinterpret_cast<const double*>(x), reinterpret_cast<double*>(out), accumulate, partials);
+  else if (c->coded)
+    ED_LAUNCH((k_spmv_csr<c128, uint16_t>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->code.p, c->lut.p,
+              reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate, partials);
+  else if (dtype == ED_F64)
+    ED_LAUNCH((k_spmv_csr<double, double>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->val.p, nullptr,
               reinterpret_cast<const double*>(x), reinterpret_cast<double*>(out), accumulate, partials);
   else if (!c->val_complex)
-    ED_LAUNCH((k_spmv_csr<c128, double>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->val.p,
+    ED_LAUNCH((k_spmv_csr<c128, double>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, c->val.p, nullptr,
               reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate, partials);
   else
-    ED_LAUNCH((k_spmv_csr<c128, c128>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, reinterpret_cast<const c128*>(c->val.p),
+    ED_LAUNCH((k_spmv_csr<c128, c128>), grid, 256, 0, n, c->row_lo, c->rowptr.p, c->col.p, reinterpret_cast<const c128*>(c->val.p), nullptr,
               reinterpret_cast<const c128*>(x), reinterpret_cast<c128*>(out), accumulate, partials);
   if (alpha_dot) ed_reduce_pairs(partials, grid, alpha_dot);
 }

@@ -238,7 +238,7 @@ k5_filter(LookupDesc L, const uint64_t* __restrict__ parent_words, int64_t lo, i
     if (ok && L.kind != ED_BASIS_FULL) {
       // the reference looks every image of a representative up in the parent and throws KeyError when absent (:81)
       for (int g = 1; g < S.n_ops; ++g)
-        if (rank_word_dyn(L, sym_apply(S, g, s)) < 0) outside = true;
+        if (!in_basis_dyn(L, sym_apply(S, g, s))) outside = true;
     }
     cand[i] = s;
     flag[i] = ok ? 1 : 0;

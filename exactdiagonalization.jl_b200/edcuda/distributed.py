@@ -215,6 +215,12 @@ class ShardedOperator:
         check(lib.ed_apply_sharded(self._handle, y._handle, x._handle, 0 if fence else 1, None))
         return None
 
+    def profile(self, y: DistributedVector, x: DistributedVector) -> dict:
+        """one matvec taken apart (halo exchange): ms of pack / fence / peer copies alone / kernels alone, max over ranks"""
+        ms = (C.c_double * 4)()
+        check(lib.ed_sharded_profile(self._handle, y._handle, x._handle, ms))
+        return {"pack_ms": ms[0], "fence_ms": ms[1], "pull_ms": ms[2], "kernel_ms": ms[3]}
+
     def lanczos(self, n_steps: int, seed: int = 0, v0: Optional[DistributedVector] = None, n_ritz: int = 4):
         alpha, beta = np.zeros(n_steps), np.zeros(n_steps)
         n_ritz = min(n_ritz, n_steps)

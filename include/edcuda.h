@@ -336,6 +336,9 @@ int ed_dvec_download(ed_dvec* v, void* host_full);
  * receives <x, Hx> summed over all rows.  no_fence != 0 skips the stream-ordered barrier that publishes x to the peers
  * (allowed when a collective already ran on every rank's stream after x was last written). */
 int ed_apply_sharded(ed_sharded* sh, ed_dvec* y, ed_dvec* x, int32_t no_fence, double* dot_out);
+/* One matvec taken apart (halo exchange only; phases that overlap in ed_apply_sharded run back to back here):
+ * ms4 = {owner-side pack, fence, all peer copies alone, all kernel chunks with the halo in place}, each max over ranks. */
+int ed_sharded_profile(ed_sharded* sh, ed_dvec* y, ed_dvec* x, double* ms4);
 /* ed_lanczos over the shards: Krylov vectors stay distributed and device resident, the two scalars of every step are
  * all-reduced (NCCL), no host synchronisation inside the loop.  v0 NULL = Philox vector from seed.  ms_per_step (may
  * be NULL) = device time per step, max over ranks. */

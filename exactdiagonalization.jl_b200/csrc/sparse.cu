@@ -85,6 +85,104 @@ k4_merge_chop(int64_t n_cols, const int64_t* __restrict__ offs, int64_t* __restr
   }
 }
 
+// The same merge with one WARP per column: the column's raw entries are ranked in shared memory (stable: equal rows keep
+// their term order), every run of equal rows is summed front to back by the lane that holds its head -- the same addition
+// order as the Dict of the reference and as k4_merge_chop, so the values are bit-identical -- chopped and compacted with
+// warp ballots.  O(n^2 / 32) comparisons per lane instead of a thread-serial insertion sort through global memory;
+// columns with more than K4_MAXN raw entries take the serial path on lane 0.
+#define K4_MAXN 256
+__global__ void __launch_bounds__(128)
+k4_merge_chop_warp(int64_t n_cols, const int64_t* __restrict__ offs, int64_t* __restrict__ raw_row,
+                   c128* __restrict__ raw_val, double tol, int is_complex, int64_t* __restrict__ kept) {
+  extern __shared__ __align__(16) unsigned char k4_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint64_t* skey = reinterpret_cast<uint64_t*>(k4_smem) + (size_t)wid * 2 * K4_MAXN;
+  uint64_t* okey = skey + K4_MAXN;
+  c128* sval = reinterpret_cast<c128*>(reinterpret_cast<uint64_t*>(k4_smem) + (size_t)(blockDim.x >> 5) * 2 * K4_MAXN) + (size_t)wid * 2 * K4_MAXN;
+  c128* oval = sval + K4_MAXN;
+  const uint64_t BIG = ~0ull;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t k = warp0; k < n_cols; k += nwarps) {
+    const int64_t lo = offs[k], hi = offs[k + 1];
+    const int n = (int)(hi - lo);
+    if (n > K4_MAXN) {                     // rare: serial path (same algorithm as k4_merge_chop)
+      if (lane == 0) {
+        for (int64_t p = lo + 1; p < hi; ++p) {
+          int64_t r = raw_row[p];
+          c128 v = raw_val[p];
+          uint64_t key = r < 0 ? BIG : (uint64_t)r;
+          int64_t q = p - 1;
+          while (q >= lo) {
+            int64_t rq = raw_row[q];
+            uint64_t kq = rq < 0 ? BIG : (uint64_t)rq;
+            if (kq <= key) break;
+            raw_row[q + 1] = rq;
+            raw_val[q + 1] = raw_val[q];
+            --q;
+          }
+          raw_row[q + 1] = r;
+          raw_val[q + 1] = v;
+        }
+        int64_t w = lo, p = lo;
+        while (p < hi && raw_row[p] >= 0) {
+          const int64_t r = raw_row[p];
+          c128 s = raw_val[p];
+          ++p;
+          while (p < hi && raw_row[p] == r) { s = cadd(s, raw_val[p]); ++p; }
+          const double mag = is_complex ? hypot(s.re, s.im) : fabs(s.re);
+          if (!(mag < tol)) { raw_row[w] = r; raw_val[w] = s; ++w; }
+        }
+        kept[k] = w - lo;
+      }
+      __syncwarp();
+      continue;
+    }
+    for (int i = lane; i < n; i += 32) {
+      const int64_t r = raw_row[lo + i];
+      skey[i] = r < 0 ? BIG : (uint64_t)r;
+      sval[i] = raw_val[lo + i];
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {       // stable rank
+      const uint64_t key = skey[i];
+      int r = 0;
+      for (int j = 0; j < n; ++j) {
+        const uint64_t kj = skey[j];
+        r += (kj < key || (kj == key && j < i)) ? 1 : 0;
+      }
+      okey[r] = key;
+      oval[r] = sval[i];
+    }
+    __syncwarp();
+    int w = 0;                                  // survivors written so far (warp-uniform)
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      bool keep = false;
+      uint64_t key = BIG;
+      c128 sum = make_c128(0.0, 0.0);
+      if (i < n) {
+        key = okey[i];
+        if (key != BIG && (i == 0 || okey[i - 1] != key)) {     // head of a run of equal rows
+          sum = oval[i];
+          for (int j = i + 1; j < n && okey[j] == key; ++j) sum = cadd(sum, oval[j]);    // term order
+          const double mag = is_complex ? hypot(sum.re, sum.im) : fabs(sum.re);
+          keep = !(mag < tol);                                    // choptol! deletes abs(v) < tol
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        const int at = w + __popc(m & ((1u << lane) - 1u));
+        raw_row[lo + at] = (int64_t)key;
+        raw_val[lo + at] = sum;
+      }
+      w += __popc(m);
+    }
+    if (lane == 0) kept[k] = w;
+    __syncwarp();
+  }
+}
+
 __global__ void __launch_bounds__(128)
 k4_gather(int64_t n_cols, const int64_t* __restrict__ offs, const int64_t* __restrict__ raw_row,
           const c128* __restrict__ raw_val, const int64_t* __restrict__ out_offs /* 0-based, relative */,
@@ -153,7 +251,12 @@ static void assemble_lines(ed_oprep* o, double tol, int side, int64_t lo, int64_
     const int64_t staged_min = getenv("EDCUDA_K6_MIN_ROWS") ? atoll(getenv("EDCUDA_K6_MIN_ROWS")) : 2048;
     if (!(o->rbasis && nc >= staged_min && ed_reduced_fill_raw_staged(o, side, lo + c0, nc, offs.p, raw_row.p, raw_val.p)))
       ED_LAUNCH(k4_fill_raw, grid, 128, 0, W, lo + c0, nc, offs.p, raw_row.p, raw_val.p);
-    ED_LAUNCH(k4_merge_chop, grid, 128, 0, nc, offs.p, raw_row.p, raw_val.p, tol, cplx, kept.p);
+    if (getenv("EDCUDA_SPARSE_SERIAL_MERGE")) {
+      ED_LAUNCH(k4_merge_chop, grid, 128, 0, nc, offs.p, raw_row.p, raw_val.p, tol, cplx, kept.p);
+    } else {       // warp per column, 4 warps per CTA, 12 KB of shared memory per warp
+      const int grid_w = (int)std::max<int64_t>(1, std::min<int64_t>((nc + 3) / 4, (int64_t)ed_sm_count() * 16));
+      ED_LAUNCH(k4_merge_chop_warp, grid_w, 128, (size_t)4 * 2 * K4_MAXN * (sizeof(uint64_t) + sizeof(c128)), nc, offs.p, raw_row.p, raw_val.p, tol, cplx, kept.p);
+    }
     exclusive_scan(kept.p, out_offs.p, nc + 1, tmp);
     int64_t nnz_b = 0;
     ED_CUDA(cudaMemcpyAsync(&nnz_b, out_offs.p + nc, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));

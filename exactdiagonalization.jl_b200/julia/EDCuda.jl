@@ -355,8 +355,100 @@ function cache_matrix!(opr, side::Cint=SIDE_LEFT)
 end
 drop_cache!(opr) = (check(ccall((:ed_oprep_drop_cache, libedcuda), Cint, (Ptr{Cvoid},), opr.ptr)); opr)
 
-# Row shard of a representation (one process per GPU): apply!/mul! then read the full x and write rows lo+1:hi of out.
+# Row shard of a representation: apply!/mul! then read the full x and write rows lo+1:hi of out.
 set_rows!(opr, lo::Integer, hi::Integer) =
     (check(ccall((:ed_oprep_set_rows, libedcuda), Cint, (Ptr{Cvoid}, Int64, Int64), opr.ptr, lo, hi)); opr)
+
+# ---------------------------------------------------------------------------------------------------------------
+# isinvariant(hs, symop, op) for every element at once (Symmetry/symmetry_apply.jl:110-135).  `represent(rhsr, op)`
+# above already fails with ArgumentError for a non-invariant operator (ed_oprep_create_reduced runs this check on the
+# host before any kernel is launched); this is the explicit form.
+function isinvariant_all(rhsr::GpuReducedHilbertSpaceRepresentation, op::ED.AbstractOperator; tol::Real=Base.rtoldefault(Float64))
+    oh = OperatorHandle(op)
+    inv = Ref{Int32}(0); bad = Ref{Int32}(-1)
+    check(ccall((:ed_operator_isinvariant, libedcuda), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Ref{Int32}, Ref{Int32}),
+                rhsr.parent.space.ptr, rhsr.symptr, oh.ptr, Float64(tol), inv, bad))
+    return inv[] != 0, Int(bad[]) + 1          # (invariant?, 1-based index of the first violating element or 0)
+end
+
+# ---------------------------------------------------------------------------------------------------------------
+# Checkpoints (not in the reference): raw binary files bound to the Hilbert space / symmetry by hashes.
+save(hsr::GpuHilbertSpaceRepresentation, path::AbstractString) =
+    check(ccall((:ed_basis_save, libedcuda), Cint, (Ptr{Cvoid}, Cstring), hsr.ptr, path))
+save(r::GpuReducedHilbertSpaceRepresentation, path::AbstractString) =
+    check(ccall((:ed_rbasis_save, libedcuda), Cint, (Ptr{Cvoid}, Cstring), r.ptr, path))
+function load_basis(hs::ED.AbstractHilbertSpace, path::AbstractString, ::Type{BR}=UInt) where {BR<:Unsigned}
+    space = SpaceHandle(ED.basespace(hs)); out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ed_basis_load, libedcuda), Cint, (Ptr{Cvoid}, Cstring, Ref{Ptr{Cvoid}}), space.ptr, path, out))
+    return _wrap_basis(hs, space, out[], BR)
+end
+
+# ---------------------------------------------------------------------------------------------------------------
+# Multi-GPU (not in the reference, whose apply! spreads rows over Threads.@threads:
+# Representation/abstract_operator_representation.jl:260-267, 358-378).  One Julia process drives all GPUs:
+#
+#     ctx  = EDCuda.Context([0, 1, 2, 3])                       # ed_ctx_create: ncclCommInitAll inside the library
+#     sh   = EDCuda.ShardedOperator(ctx, dev -> EDCuda.represent(EDCuda.represent(sector), H))
+#     x, y = EDCuda.DVector(sh), EDCuda.DVector(sh);  EDCuda.upload!(x, x_host)
+#     mul!(y, sh, x);  EDCuda.download!(y_host, y);  res = EDCuda.lanczos(sh, 100)
+#
+# The row partition, the halo exchange over NVLink and the NCCL collectives all live in libedcuda.so.
+mutable struct Context
+    ptr::Ptr{Cvoid}; devices::Vector{Int32}
+    function Context(devices::AbstractVector{<:Integer})
+        out = Ref{Ptr{Cvoid}}(C_NULL); d = Int32.(devices)
+        check(ccall((:ed_ctx_create, libedcuda), Cint, (Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), length(d), d, out))
+        c = new(out[], d)
+        finalizer(x -> ccall((:ed_ctx_destroy, libedcuda), Cint, (Ptr{Cvoid},), x.ptr), c)
+        return c
+    end
+end
+
+mutable struct ShardedOperator{S}
+    ptr::Ptr{Cvoid}; ctx::Context; oprs::Vector{Any}; dim::Int
+end
+# make(dev) builds the representation on device `dev` (the library's current device is set before the call)
+function ShardedOperator(ctx::Context, make::Function; exchange::Integer=0, chunks::Integer=0)
+    oprs = Any[]
+    for dev in ctx.devices
+        check(ccall((:ed_set_device, libedcuda), Cint, (Cint,), dev))
+        push!(oprs, make(dev))
+    end
+    S = eltype(oprs[1]); out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:ed_sharded_create, libedcuda), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, Int32, Int32, Ref{Ptr{Cvoid}}),
+                ctx.ptr, Ptr{Cvoid}[o.ptr for o in oprs], dtype_code(S), exchange, chunks, out))
+    sh = ShardedOperator{S}(out[], ctx, oprs, size(oprs[1], 1))
+    finalizer(x -> ccall((:ed_sharded_destroy, libedcuda), Cint, (Ptr{Cvoid},), x.ptr), sh)
+    return sh
+end
+
+mutable struct DVector{S}
+    ptr::Ptr{Cvoid}; sh::ShardedOperator{S}
+    function DVector(sh::ShardedOperator{S}) where {S}
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:ed_dvec_create, libedcuda), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), sh.ptr, out))
+        v = new{S}(out[], sh)
+        finalizer(x -> ccall((:ed_dvec_destroy, libedcuda), Cint, (Ptr{Cvoid},), x.ptr), v)
+        return v
+    end
+end
+upload!(v::DVector{S}, host::Vector{S}) where {S} =
+    (length(host) == v.sh.dim || throw(DimensionMismatch("vector length differs from the dimension"));
+     check(ccall((:ed_dvec_upload, libedcuda), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.ptr, host)); v)
+download!(host::Vector{S}, v::DVector{S}) where {S} =
+    (check(ccall((:ed_dvec_download, libedcuda), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.ptr, host)); host)
+
+function LinearAlgebra.mul!(y::DVector{S}, sh::ShardedOperator{S}, x::DVector{S}) where {S}
+    check(ccall((:ed_apply_sharded, libedcuda), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ptr{Float64}), sh.ptr, y.ptr, x.ptr, 0, C_NULL))
+    return y
+end
+
+function lanczos(sh::ShardedOperator{S}, nsteps::Integer; seed::Integer=0, nritz::Integer=4) where {S}
+    alpha = zeros(nsteps); beta = zeros(nsteps); ritz = zeros(nritz); done = Ref{Int32}(0); ms = Ref{Float64}(0.0)
+    check(ccall((:ed_lanczos_sharded, libedcuda), Cint,
+                (Ptr{Cvoid}, Int32, UInt64, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{Int32}, Ref{Float64}),
+                sh.ptr, nsteps, seed, C_NULL, alpha, beta, ritz, nritz, done, ms))
+    return (alpha=alpha[1:done[]], beta=beta[1:done[]], ritz=ritz, ms_per_step=ms[])
+end
 
 end # module

@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--impl", default="edcuda")
     ap.add_argument("--workload", default="xxz_chain_L32_sz0")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "allgather"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "push", "pull", "allgather"],
                     help="N>1: how remote rows of x reach a rank: halo copies over NVLink (packed by the owner, pulled by copy engines) or an NCCL all-gather per matvec")
     ap.add_argument("--chunks", type=int, default=0, help="N>1: launch chunks per matvec (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -460,11 +460,13 @@ def main():
         halo_max = int(ctx.allreduce([float(info["n_halo"])], "max")[0])
         phases = sh.profile(yv, xv) if info["exchange"] == "halo" else None
         details.update({"rows_per_gpu": n_local, "sharding": "tiles assigned by the library's planner (ed_u1_shard_layout)" if info["exchange"] == "halo" else "contiguous row ranges",
-                        "exchange": ("owner-side pack + copy-engine pulls of the packed tiles over NVLink into a halo buffer, %d launch chunks, one NCCL fence per matvec" % info["n_chunks"])
+                        "exchange": ("halo exchange over NVLink (%s), interior tiles first, %d launch chunks, one NCCL fence per matvec" % (
+                                     "owners write the tiles their peers read into the peers' halo buffers with remote stores and bump a per-chunk arrival counter"
+                                     if info["halo_transport"] == "owner pushes" else "owner-side pack + copy-engine pulls of the packed tiles", info["n_chunks"]))
                         if info["exchange"] == "halo" else "NCCL all-gather of x per matvec", "halo_rows_max": halo_max,
                         "nvlink_bytes_per_rank_per_matvec_max": halo_max * 8, "pulls_per_matvec": info["n_pulls"],
                         "phases_run_back_to_back_ms": phases,
-                        "pull_GBps_per_rank": (halo_max * 8 / (phases["pull_ms"] * 1e-3) / 1e9) if phases and phases["pull_ms"] > 0 else None,
+                        "halo_GBps_per_rank": (halo_max * 8 / (phases["pull_ms"] * 1e-3) / 1e9) if phases and phases["pull_ms"] > 0 else None,
                         "nccl_version": ctx.nccl_version, "collectives": "in-library NCCL (no torch.distributed on the data path)",
                         "kernel": "generic term-walk (k2_apply_generic)" if args.kernel == 1 else "tiled U(1) kernel k2_apply_u1"})
     value = 1e3 / ms_per_step

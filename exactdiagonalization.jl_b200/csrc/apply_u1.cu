@@ -1302,6 +1302,27 @@ void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunk
     halo += len;
   }
   S.n_halo = halo;
+  S.chunk_halo_rows.assign(G.n_chunks, 0);
+  for (size_t i = 0; i < ht.size(); ++i) S.chunk_halo_rows[hc[i]] += (int64_t)plan->h_size[ht[i]];
+  // pushes: the receivers' halo tiles owned by this rank with their offsets in the RECEIVER's halo, earliest chunk first
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    const auto& rt = G.halo_tiles[r];
+    int64_t at = 0;
+    for (size_t i = 0; i < rt.size(); ++i) {
+      const uint32_t t = rt[i];
+      const int64_t len = (int64_t)plan->h_size[t];
+      if (G.owner[t] == rank) {
+        const int ch = G.halo_chunk[r][i];
+        if (!S.pushes.empty() && S.pushes.back().recv == r && S.pushes.back().chunk == ch && S.pushes.back().src_off + S.pushes.back().len == G.off[t] &&
+            S.pushes.back().dst_off + S.pushes.back().len == at)
+          S.pushes.back().len += len;
+        else S.pushes.push_back({r, ch, G.off[t], at, len});
+      }
+      at += len;
+    }
+  }
+  std::stable_sort(S.pushes.begin(), S.pushes.end(), [](const U1Push& a, const U1Push& b) { return a.chunk < b.chunk; });
   // packs: for every receiver (ascending) and chunk, its halo tiles owned by this rank, in its halo order
   int64_t send = 0;
   for (int r = 0; r < world; ++r) {
@@ -1417,7 +1438,7 @@ void ed_apply_u1_sharded(ed_oprep* o, int dtype, const U1ShardLaunch& L) {
 // Host-only description of the shard layout (no device needed): what tests/test_shard_plan.py replays on CPU with gloo.
 extern "C" int ed_shard_plan_describe(const ed_operator* op, int32_t n_bits, int32_t n_set, int32_t dtype, int32_t world, int32_t rank,
                                       int32_t n_chunks, int32_t policy, int64_t* counts, int64_t* ranges, int64_t* tiles,
-                                      int64_t* pulls, int64_t* packs, int64_t* reads) {
+                                      int64_t* pulls, int64_t* packs, int64_t* reads, int64_t* pushes) {
   ED_TRY
   ED_REQUIRE(op && counts, ED_ERR_ARGUMENT, "null argument");
   ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
@@ -1443,7 +1464,12 @@ extern "C" int ed_shard_plan_describe(const ed_operator* op, int32_t n_bits, int
   for (uint64_t v : plan->h_size) dim += v;
   counts[0] = S.n_local; counts[1] = S.n_halo; counts[2] = (int64_t)S.range_lo.size(); counts[3] = (int64_t)S.tile_H.size();
   counts[4] = (int64_t)S.pulls.size(); counts[5] = n_reads; counts[6] = S.n_chunks; counts[7] = (int64_t)dim;
-  counts[8] = (int64_t)S.packs.size(); counts[9] = S.n_send;
+  counts[8] = (int64_t)S.packs.size(); counts[9] = S.n_send; counts[10] = (int64_t)S.pushes.size(); counts[11] = 0;
+  if (pushes)
+    for (size_t i = 0; i < S.pushes.size(); ++i) {
+      pushes[5 * i] = S.pushes[i].recv; pushes[5 * i + 1] = S.pushes[i].chunk; pushes[5 * i + 2] = S.pushes[i].src_off;
+      pushes[5 * i + 3] = S.pushes[i].dst_off; pushes[5 * i + 4] = S.pushes[i].len;
+    }
   if (packs)
     for (size_t i = 0; i < S.packs.size(); ++i) { packs[3 * i] = S.packs[i].src_off; packs[3 * i + 1] = S.packs[i].dst_off; packs[3 * i + 2] = S.packs[i].len; }
   if (ranges) for (size_t k = 0; k < S.range_lo.size(); ++k) { ranges[2 * k] = S.range_lo[k]; ranges[2 * k + 1] = S.range_hi[k]; }

@@ -82,6 +82,7 @@ struct CtxRank {
   int rank = 0, device = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy[ED_CTX_PULL_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t push = nullptr;                   // high priority: the push kernel must get SM slots beside the compute kernels
   ncclComm_t comm = nullptr;
   cudaEvent_t ev = nullptr;                      // scratch event (loopback joins, fences)
   cudaEvent_t timer[ED_CTX_TIMER_SLOTS] = {nullptr};
@@ -198,6 +199,7 @@ void ctx_sync(ed_ctx* c) {
   for (auto& r : c->local) {
     ED_CUDA(cudaSetDevice(r.device));
     for (int s = 0; s < ED_CTX_PULL_STREAMS; ++s) ED_CUDA(cudaStreamSynchronize(r.copy[s]));
+    ED_CUDA(cudaStreamSynchronize(r.push));
     ED_CUDA(cudaStreamSynchronize(r.stream));
   }
 }
@@ -214,6 +216,11 @@ void ctx_init_rank(ed_ctx* c, CtxRank& r) {
   ED_CUDA(cudaSetDevice(r.device));
   ED_CUDA(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
   for (int s = 0; s < ED_CTX_PULL_STREAMS; ++s) ED_CUDA(cudaStreamCreateWithFlags(&r.copy[s], cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;
+    ED_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    ED_CUDA(cudaStreamCreateWithPriority(&r.push, cudaStreamNonBlocking, hi));
+  }
   ED_CUDA(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
   for (int t = 0; t < ED_CTX_TIMER_SLOTS; ++t) ED_CUDA(cudaEventCreate(&r.timer[t]));
   ED_CUDA(cudaMalloc(&r.scalars, 8 * sizeof(double)));
@@ -237,6 +244,14 @@ struct ShardRank {
   std::vector<void*> opened;                     // IPC mappings to close
   DevBuf<int64_t> d_packs;                       // [3 * n_pack_items] (src, dst, len), items of at most PACK_ITEM elements
   int n_pack_items = 0;
+  // push exchange: the halo (+ one arrival counter per launch chunk behind it) is what the peers map and write
+  void* halo_mem = nullptr;
+  unsigned long long* counters = nullptr;        // [n_chunks] rows that have arrived for each chunk, cumulative over matvecs
+  std::vector<void*> peer_halo;                  // [world]
+  DevBuf<int64_t> d_push;                        // [4 * n_push_items] (src offset, destination address, rows, counter address)
+  int n_push_items = 0;
+  unsigned long long seq = 0;                    // matvecs pushed so far
+  DevBuf<int> wait_error;                        // set by a wait that timed out
   DevBuf<double> partials;
   std::vector<cudaEvent_t> ev_pull;      // [n_chunks * n_pull_streams]
   // all-gather exchange
@@ -250,6 +265,7 @@ struct ed_sharded {
   ed_ctx* ctx = nullptr;
   int dtype = ED_F64;
   bool halo = false;
+  bool push = false;                         // halo exchange by owner-side pushes (remote stores + arrival counters)
   int64_t dim = 0;
   size_t es = 8;
   std::vector<ShardRank> r;                  // per local rank
@@ -265,6 +281,38 @@ struct ed_dvec {
 
 #define PACK_ITEM 4096
 
+// PUSH exchange: the owner writes the tiles a peer reads straight into that peer's halo buffer over NVLink (remote
+// stores are posted: no round trip per access, unlike peer loads or copy-engine reads), one CTA per item of <= PACK_ITEM
+// rows, items ordered by the receiver's launch chunk.  After its stores every thread fences at system scope; then one
+// thread adds the item's row count to the receiver's arrival counter of that chunk (a remote atomic).  The receiver's
+// stream waits (k_wait_rows) until the counter has reached seq * (rows the chunk needs): everything this kernel and the
+// kernels behind the wait need is ordered by fence + atomic on the sender and by the kernel boundary on the receiver.
+template <typename VecT>
+__global__ void __launch_bounds__(256) k_push(const VecT* __restrict__ x, const int64_t* __restrict__ items) {
+  const int64_t* it = items + 4 * (int64_t)blockIdx.x;
+  const VecT* src = x + it[0];
+  VecT* dst = reinterpret_cast<VecT*>(it[1]);
+  const int len = (int)it[2];
+  for (int i = threadIdx.x; i < len; i += 256) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd_system(reinterpret_cast<unsigned long long*>(it[3]), (unsigned long long)len);
+}
+
+// one thread polls the arrival counter of a launch chunk; gives up after ~20 s (sets *err) instead of hanging the GPU
+__global__ void k_wait_rows(const unsigned long long* counter, unsigned long long target, int* err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const volatile unsigned long long* c = counter;
+  unsigned long long t0 = 0, now = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while (*c < target) {
+    __nanosleep(500);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - t0 > 20000000000ull) { *err = 1; break; }
+  }
+  __threadfence_system();
+}
+
 // owner-side packing: the tiles the peers read, gathered from x into the send buffer (one CTA per item of <= PACK_ITEM elements)
 template <typename VecT>
 __global__ void __launch_bounds__(256) k_pack(const VecT* __restrict__ x, VecT* __restrict__ send, const int64_t* __restrict__ items) {
@@ -279,6 +327,24 @@ namespace {
 void sharded_pack(ed_sharded* S, ed_dvec* x) {
   if (!S->halo || S->ctx->world == 1) return;
   ed_ctx* c = S->ctx;
+  if (S->push) {
+    // x of every rank is final at this point of its main stream, and every peer is done with its previous halo (a
+    // collective ran after its last kernel): start writing the peers' halos on the high-priority stream
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = S->r[i];
+      ++Q.seq;
+      if (!Q.n_push_items) continue;
+      ED_CUDA(cudaSetDevice(R.device));
+      ED_CUDA(cudaEventRecord(R.ev, R.stream));
+      ED_CUDA(cudaStreamWaitEvent(R.push, R.ev, 0));
+      ed_push_stream(R.push);
+      if (S->dtype == ED_F64) ED_LAUNCH(k_push<double>, Q.n_push_items, 256, 0, reinterpret_cast<const double*>(x->local[i]), Q.d_push.p);
+      else ED_LAUNCH(k_push<double2>, Q.n_push_items, 256, 0, reinterpret_cast<const double2*>(x->local[i]), Q.d_push.p);
+      ed_pop_stream();
+    }
+    return;
+  }
   S->parity ^= 1;
   for (size_t i = 0; i < c->local.size(); ++i) {
     ShardRank& Q = S->r[i];
@@ -293,7 +359,40 @@ void sharded_pack(ed_sharded* S, ed_dvec* x) {
 void sharded_apply(ed_sharded* S, ed_dvec* y, ed_dvec* x, bool packed, bool want_dot) {
   ed_ctx* c = S->ctx;
   DeviceGuard g;
-  if (S->halo) {
+  if (S->halo && S->push) {
+    if (!packed) {
+      ctx_fence(c);          // every rank is done with its previous halo and its x is final
+      sharded_pack(S, x);
+    }
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = S->r[i];
+      RankScope scope(R);
+      for (int ch = 0; ch < Q.L.n_chunks; ++ch) {
+        if (c->world > 1 && Q.L.chunk_halo_rows[ch] > 0)
+          ED_LAUNCH(k_wait_rows, 1, 32, 0, Q.counters + ch, Q.seq * (unsigned long long)Q.L.chunk_halo_rows[ch], Q.wait_error.p);
+        U1ShardLaunch A;
+        A.tile_H = Q.d_tile_H.p;
+        A.first = Q.L.chunk_first[ch];
+        A.count = Q.L.chunk_first[ch + 1] - Q.L.chunk_first[ch];
+        A.dir = Q.d_dir.p;
+        A.x_local = x->local[i];
+        A.x_halo = Q.halo_mem;
+        A.y_local = y->local[i];
+        A.stream_mode = 0;
+        A.accumulate = 0;
+        A.partials = want_dot ? Q.partials.p : nullptr;
+        ed_apply_u1_sharded(Q.op, S->dtype, A);
+      }
+      if (want_dot) {
+        if (Q.L.tile_H.empty()) ED_CUDA(cudaMemsetAsync(Q.dot.p, 0, 2 * sizeof(double), R.stream));
+        else ed_reduce_pairs(Q.partials.p, (int)Q.L.tile_H.size(), Q.dot.p);
+      }
+      // the next push may overwrite x's successor only after this rank's push kernel has read x: order it behind
+      ED_CUDA(cudaEventRecord(R.ev, R.push));
+      ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
+    }
+  } else if (S->halo) {
     if (!packed) {
       sharded_pack(S, x);
       ctx_fence(c);          // every rank's send buffer is complete, and every rank is done with the previous halo
@@ -365,6 +464,17 @@ void sharded_apply(ed_sharded* S, ed_dvec* y, ed_dvec* x, bool packed, bool want
     std::vector<double*> bufs;
     for (auto& Q : S->r) bufs.push_back(Q.dot.p);
     ctx_allreduce(c, bufs, 2, 0);
+  }
+}
+
+// a wait that timed out (a peer never delivered its tiles) is reported at the next host synchronisation
+void check_wait_error(ed_sharded* S) {
+  if (!S->halo || !S->push) return;
+  for (size_t i = 0; i < S->r.size(); ++i) {
+    RankScope scope(S->ctx->local[i]);
+    int e = 0;
+    S->r[i].wait_error.download(&e, 1);
+    ED_REQUIRE(e == 0, ED_ERR_CUDA, "halo exchange timed out: a peer rank did not deliver its tiles within 20 s");
   }
 }
 
@@ -453,6 +563,7 @@ int ed_ctx_destroy(ed_ctx* ctx) {
     cudaStreamSynchronize(r.stream);
     if (r.comm) nccl().CommDestroy(r.comm);
     for (int s = 0; s < ED_CTX_PULL_STREAMS; ++s) if (r.copy[s]) cudaStreamDestroy(r.copy[s]);
+    if (r.push) cudaStreamDestroy(r.push);
     if (r.stream) cudaStreamDestroy(r.stream);
     if (r.ev) cudaEventDestroy(r.ev);
     for (int t = 0; t < ED_CTX_TIMER_SLOTS; ++t) if (r.timer[t]) cudaEventDestroy(r.timer[t]);
@@ -552,7 +663,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   ED_TRY
   ED_REQUIRE(ctx && opreps && out, ED_ERR_ARGUMENT, "null argument");
   ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
-  ED_REQUIRE(exchange >= 0 && exchange <= 2, ED_ERR_ARGUMENT, "exchange: 0 automatic, 1 NCCL all-gather, 2 halo copies");
+  ED_REQUIRE(exchange >= 0 && exchange <= 3, ED_ERR_ARGUMENT, "exchange: 0 automatic, 1 NCCL all-gather, 2 halo by copy-engine pulls, 3 halo by owner pushes");
   DeviceGuard g;
   std::unique_ptr<ed_sharded> S(new ed_sharded());
   S->ctx = ctx;
@@ -573,8 +684,9 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
     ED_REQUIRE(opreps[i]->dim == S->dim, ED_ERR_DIMENSION_MISMATCH, "the per-rank representations differ");
     fast = fast && !opreps[i]->rbasis && opreps[i]->kernel_choice == 0 && !opreps[i]->csr[0] && ed_apply_u1_supported(opreps[i], dtype, ED_SIDE_LEFT);
   }
-  ED_REQUIRE(exchange != 2 || fast, ED_ERR_UNSUPPORTED, "the halo exchange is defined for the tiled U(1) kernel only");
+  ED_REQUIRE(exchange < 2 || fast, ED_ERR_UNSUPPORTED, "the halo exchange is defined for the tiled U(1) kernel only");
   S->halo = fast && exchange != 1;
+  S->push = S->halo && exchange != 2 && !getenv("EDCUDA_SHARD_PULL");
   S->rows_of_rank.assign(ctx->world, 0);
   for (int i = 0; i < nl; ++i) {
     CtxRank& R = ctx->local[i];
@@ -590,9 +702,19 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
       S->rows_of_rank = Q.L.rows_of_rank;
       Q.d_tile_H.upload(Q.L.tile_H);
       Q.d_dir.upload(Q.L.dir);
-      Q.halo.alloc((size_t)std::max<int64_t>(Q.L.n_halo, 1) * S->es);
-      for (int b = 0; b < 2; ++b) ED_CUDA(cudaMalloc(&Q.send[b], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
-      {
+      Q.wait_error.alloc(1);
+      ED_CUDA(cudaMemsetAsync(Q.wait_error.p, 0, sizeof(int), R.stream));
+      if (S->push) {
+        // halo + arrival counters in ONE allocation: one IPC mapping per peer covers both
+        const size_t halo_bytes = (((size_t)std::max<int64_t>(Q.L.n_halo, 1) * S->es) + 255) & ~(size_t)255;
+        ED_CUDA(cudaMalloc(&Q.halo_mem, halo_bytes + (size_t)Q.L.n_chunks * sizeof(unsigned long long)));
+        Q.counters = reinterpret_cast<unsigned long long*>(static_cast<char*>(Q.halo_mem) + halo_bytes);
+        ED_CUDA(cudaMemsetAsync(Q.counters, 0, (size_t)Q.L.n_chunks * sizeof(unsigned long long), R.stream));
+      } else {
+        Q.halo.alloc((size_t)std::max<int64_t>(Q.L.n_halo, 1) * S->es);
+        for (int b = 0; b < 2; ++b) ED_CUDA(cudaMalloc(&Q.send[b], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
+      }
+      if (!S->push) {
         std::vector<int64_t> items;
         for (const U1Pack& p : Q.L.packs)
           for (int64_t o = 0; o < p.len; o += PACK_ITEM) { items.push_back(p.src_off + o); items.push_back(p.dst_off + o); items.push_back(std::min<int64_t>(PACK_ITEM, p.len - o)); }
@@ -622,36 +744,81 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   S->row_offset.assign(ctx->world + 1, 0);
   for (int r = 0; r < ctx->world; ++r) S->row_offset[r + 1] = S->row_offset[r] + S->rows_of_rank[r];
   ED_REQUIRE(S->row_offset[ctx->world] == S->dim, ED_ERR_INTERNAL, "the shards do not cover the basis");
-  if (S->halo) {
-    // every rank sees every rank's send buffers: directly (one process) or through CUDA IPC (process per GPU)
-    for (int b = 0; b < 2; ++b) {
-      for (int i = 0; i < nl; ++i) S->r[i].peer_send[b].assign(ctx->world, nullptr);
-      if (!ctx->multi_process) {
-        for (int i = 0; i < nl; ++i)
-          for (int j = 0; j < nl; ++j) S->r[i].peer_send[b][ctx->local[j].rank] = S->r[j].send[b];
-      } else if (ctx->world > 1) {
-        CtxRank& R = ctx->local[0];
-        ShardRank& Q = S->r[0];
-        ED_CUDA(cudaSetDevice(R.device));
-        cudaIpcMemHandle_t mine;
-        ED_CUDA(cudaIpcGetMemHandle(&mine, Q.send[b]));
-        DevBuf<unsigned char> sbuf(64), rbuf((size_t)64 * ctx->world);
-        ED_CUDA(cudaMemcpyAsync(sbuf.p, &mine, 64, cudaMemcpyHostToDevice, R.stream));
-        ED_NCCL(nccl().AllGather(sbuf.p, rbuf.p, 64, ncclChar, R.comm, R.stream));
-        std::vector<unsigned char> all((size_t)64 * ctx->world);
-        ED_CUDA(cudaMemcpyAsync(all.data(), rbuf.p, all.size(), cudaMemcpyDeviceToHost, R.stream));
-        ED_CUDA(cudaStreamSynchronize(R.stream));
+  // every rank sees the buffers its peers read (pull: send buffers) or write (push: halos): directly when one process drives
+  // all GPUs, through CUDA IPC with one process per GPU
+  auto share = [&](const std::vector<void*>& mine /* per local rank */, std::vector<std::vector<void*>>& seen /* [local][world] */) {
+    seen.assign(nl, std::vector<void*>(ctx->world, nullptr));
+    if (!ctx->multi_process) {
+      for (int i = 0; i < nl; ++i)
+        for (int j = 0; j < nl; ++j) seen[i][ctx->local[j].rank] = mine[j];
+      return;
+    }
+    CtxRank& R = ctx->local[0];
+    ED_CUDA(cudaSetDevice(R.device));
+    if (ctx->world == 1) { seen[0][0] = mine[0]; return; }
+    cudaIpcMemHandle_t h_mine;
+    ED_CUDA(cudaIpcGetMemHandle(&h_mine, mine[0]));
+    DevBuf<unsigned char> sbuf(64), rbuf((size_t)64 * ctx->world);
+    ED_CUDA(cudaMemcpyAsync(sbuf.p, &h_mine, 64, cudaMemcpyHostToDevice, R.stream));
+    ED_NCCL(nccl().AllGather(sbuf.p, rbuf.p, 64, ncclChar, R.comm, R.stream));
+    std::vector<unsigned char> all((size_t)64 * ctx->world);
+    ED_CUDA(cudaMemcpyAsync(all.data(), rbuf.p, all.size(), cudaMemcpyDeviceToHost, R.stream));
+    ED_CUDA(cudaStreamSynchronize(R.stream));
+    for (int r = 0; r < ctx->world; ++r) {
+      if (r == R.rank) { seen[0][r] = mine[0]; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all.data() + (size_t)64 * r, 64);
+      void* p = nullptr;
+      ED_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      S->r[0].opened.push_back(p);
+      seen[0][r] = p;
+    }
+  };
+  if (S->halo && S->push) {
+    std::vector<void*> mine;
+    for (int i = 0; i < nl; ++i) mine.push_back(S->r[i].halo_mem);
+    std::vector<std::vector<void*>> seen;
+    share(mine, seen);
+    for (int i = 0; i < nl; ++i) {
+      ShardRank& Q = S->r[i];
+      RankScope scope(ctx->local[i]);
+      Q.peer_halo = seen[i];
+      // every rank's counters sit behind its halo: the offset follows from that rank's halo size (known to the planner)
+      std::vector<int64_t> items;
+      std::vector<size_t> halo_bytes_of(ctx->world, 0);
+      {
+        // halo sizes of the peers: rows pushed to r by all senders = r's n_halo; recompute from the layouts
+        FastU1Plan* plan = ed_u1_plan(Q.op, dtype);
+        const int policy = getenv("EDCUDA_SHARD_POLICY") ? atoi(getenv("EDCUDA_SHARD_POLICY")) : 0;
         for (int r = 0; r < ctx->world; ++r) {
-          if (r == R.rank) { Q.peer_send[b][r] = Q.send[b]; continue; }
-          cudaIpcMemHandle_t h;
-          memcpy(&h, all.data() + (size_t)64 * r, 64);
-          void* p = nullptr;
-          ED_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
-          Q.opened.push_back(p);
-          Q.peer_send[b][r] = p;
+          U1ShardLayout Lr;
+          ed_u1_shard_layout(plan, ctx->world, r, ctx->world > 1 ? n_chunks : 1, policy, &Lr);
+          halo_bytes_of[r] = (((size_t)std::max<int64_t>(Lr.n_halo, 1) * S->es) + 255) & ~(size_t)255;
         }
-      } else {
-        S->r[0].peer_send[b][0] = S->r[0].send[b];
+      }
+      for (const U1Push& p : Q.L.pushes)
+        for (int64_t o = 0; o < p.len; o += PACK_ITEM) {
+          items.push_back(p.src_off + o);
+          items.push_back((int64_t)(reinterpret_cast<uintptr_t>(Q.peer_halo[p.recv]) + (size_t)(p.dst_off + o) * S->es));
+          items.push_back(std::min<int64_t>(PACK_ITEM, p.len - o));
+          items.push_back((int64_t)(reinterpret_cast<uintptr_t>(Q.peer_halo[p.recv]) + halo_bytes_of[p.recv] + (size_t)p.chunk * sizeof(unsigned long long)));
+        }
+      Q.n_push_items = (int)(items.size() / 4);
+      if (items.empty()) items.assign(4, 0);
+      Q.d_push.upload(items);
+      ED_CUDA(cudaStreamSynchronize(ctx->local[i].stream));
+    }
+    ctx_fence(ctx);        // every rank's counters are zeroed before anyone pushes
+    ctx_sync(ctx);
+  } else if (S->halo) {
+    for (int b = 0; b < 2; ++b) {
+      std::vector<void*> mine;
+      for (int i = 0; i < nl; ++i) mine.push_back(S->r[i].send[b]);
+      std::vector<std::vector<void*>> seen;
+      share(mine, seen);
+      for (int i = 0; i < nl; ++i) {
+        S->r[i].peer_send[b].assign(ctx->world, nullptr);
+        for (int r = 0; r < ctx->world; ++r) S->r[i].peer_send[b][r] = seen[i][r];
       }
     }
   }
@@ -677,6 +844,8 @@ int ed_sharded_destroy(ed_sharded* sh) {
     ShardRank& Q = sh->r[i];
     for (auto& e : Q.ev_pull) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) if (Q.send[b]) cudaFree(Q.send[b]);
+    if (Q.halo_mem) cudaFree(Q.halo_mem);
+    Q.d_push.release(); Q.wait_error.release();
     Q.d_tile_H.release(); Q.d_dir.release(); Q.halo.release(); Q.partials.release(); Q.x_full.release(); Q.dot.release(); Q.d_packs.release();
   }
   delete sh;
@@ -691,9 +860,9 @@ int ed_sharded_info(const ed_sharded* sh, int32_t local_index, int64_t* n_local,
   if (n_local) *n_local = Q.n_local;
   if (n_halo) *n_halo = sh->halo ? Q.L.n_halo : (sh->ctx->world > 1 ? sh->dim - Q.n_local : 0);
   if (n_ranges) *n_ranges = (int32_t)Q.range_lo.size();
-  if (n_pulls) *n_pulls = sh->halo ? (int32_t)Q.L.pulls.size() : 0;
+  if (n_pulls) *n_pulls = sh->halo ? (int32_t)(sh->push ? Q.L.pushes.size() : Q.L.pulls.size()) : 0;
   if (n_chunks) *n_chunks = sh->halo ? Q.L.n_chunks : 1;
-  if (halo_exchange) *halo_exchange = sh->halo ? 1 : 0;
+  if (halo_exchange) *halo_exchange = sh->halo ? (sh->push ? 2 : 1) : 0;
   ED_CATCH
 }
 
@@ -829,6 +998,7 @@ int ed_apply_sharded(ed_sharded* sh, ed_dvec* y, ed_dvec* x, int32_t no_fence, d
     ED_CUDA(cudaSetDevice(R.device));
     ED_CUDA(cudaMemcpyAsync(dot_out, sh->r[0].dot.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, R.stream));
     ED_CUDA(cudaStreamSynchronize(R.stream));
+    check_wait_error(sh);
   }
   ED_CATCH
 }
@@ -842,41 +1012,62 @@ int ed_sharded_profile(ed_sharded* sh, ed_dvec* y, ed_dvec* x, double* ms4) {
   ED_REQUIRE(sh->halo, ED_ERR_UNSUPPORTED, "only the halo exchange has separate phases");
   ed_ctx* c = sh->ctx;
   DeviceGuard g;
+  auto kernels = [&]() {
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      ShardRank& Q = sh->r[i];
+      RankScope scope(c->local[i]);
+      for (int ch = 0; ch < Q.L.n_chunks; ++ch) {
+        U1ShardLaunch A;
+        A.tile_H = Q.d_tile_H.p; A.first = Q.L.chunk_first[ch]; A.count = Q.L.chunk_first[ch + 1] - Q.L.chunk_first[ch];
+        A.dir = Q.d_dir.p; A.x_local = x->local[i]; A.x_halo = sh->push ? Q.halo_mem : (void*)Q.halo.p; A.y_local = y->local[i];
+        A.stream_mode = 0; A.accumulate = 0; A.partials = nullptr;
+        ed_apply_u1_sharded(Q.op, sh->dtype, A);
+      }
+    }
+  };
   ctx_fence(c);
   ed_ctx_timer_record(c, 50);
-  sharded_pack(sh, x);
-  ed_ctx_timer_record(c, 51);
-  ctx_fence(c);
-  ed_ctx_timer_record(c, 52);
-  for (size_t i = 0; i < c->local.size(); ++i) {
-    CtxRank& R = c->local[i];
-    ShardRank& Q = sh->r[i];
-    ED_CUDA(cudaSetDevice(R.device));
-    ED_CUDA(cudaEventRecord(R.ev, R.stream));
-    ED_CUDA(cudaStreamWaitEvent(R.copy[0], R.ev, 0));
-    for (const U1Pull& p : Q.L.pulls)
-      ED_CUDA(cudaMemcpyAsync(Q.halo.p + (size_t)p.dst_off * sh->es, static_cast<const char*>(Q.peer_send[sh->parity][p.peer]) + (size_t)p.src_off * sh->es,
-                              (size_t)p.len * sh->es, cudaMemcpyDeviceToDevice, R.copy[0]));
-    ED_CUDA(cudaEventRecord(R.ev, R.copy[0]));
-    ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
-  }
-  ed_ctx_timer_record(c, 53);
-  for (size_t i = 0; i < c->local.size(); ++i) {
-    ShardRank& Q = sh->r[i];
-    RankScope scope(c->local[i]);
-    for (int ch = 0; ch < Q.L.n_chunks; ++ch) {
-      U1ShardLaunch A;
-      A.tile_H = Q.d_tile_H.p; A.first = Q.L.chunk_first[ch]; A.count = Q.L.chunk_first[ch + 1] - Q.L.chunk_first[ch];
-      A.dir = Q.d_dir.p; A.x_local = x->local[i]; A.x_halo = Q.halo.p; A.y_local = y->local[i];
-      A.stream_mode = 0; A.accumulate = 0; A.partials = nullptr;
-      ed_apply_u1_sharded(Q.op, sh->dtype, A);
+  if (sh->push) {
+    ed_ctx_timer_record(c, 51);          // no pack pass
+    ctx_fence(c);
+    ed_ctx_timer_record(c, 52);
+    sharded_pack(sh, x);                 // the push kernels
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = sh->r[i];
+      RankScope scope(R);
+      for (int ch = 0; ch < Q.L.n_chunks; ++ch)
+        if (c->world > 1 && Q.L.chunk_halo_rows[ch] > 0)
+          ED_LAUNCH(k_wait_rows, 1, 32, 0, Q.counters + ch, Q.seq * (unsigned long long)Q.L.chunk_halo_rows[ch], Q.wait_error.p);
+      ED_CUDA(cudaEventRecord(R.ev, R.push));
+      ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
+    }
+  } else {
+    sharded_pack(sh, x);
+    ed_ctx_timer_record(c, 51);
+    ctx_fence(c);
+    ed_ctx_timer_record(c, 52);
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = sh->r[i];
+      ED_CUDA(cudaSetDevice(R.device));
+      ED_CUDA(cudaEventRecord(R.ev, R.stream));
+      ED_CUDA(cudaStreamWaitEvent(R.copy[0], R.ev, 0));
+      for (const U1Pull& p : Q.L.pulls)
+        ED_CUDA(cudaMemcpyAsync(Q.halo.p + (size_t)p.dst_off * sh->es, static_cast<const char*>(Q.peer_send[sh->parity][p.peer]) + (size_t)p.src_off * sh->es,
+                                (size_t)p.len * sh->es, cudaMemcpyDeviceToDevice, R.copy[0]));
+      ED_CUDA(cudaEventRecord(R.ev, R.copy[0]));
+      ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
     }
   }
+  ed_ctx_timer_record(c, 53);
+  kernels();
   ed_ctx_timer_record(c, 54);
   for (int k = 0; k < 4; ++k) {
     const int rc = ed_ctx_timer_elapsed(c, 50 + k, 51 + k, ms4 + k);
     ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
   }
+  check_wait_error(sh);
   ED_CATCH
 }
 
@@ -887,6 +1078,7 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
   ed_ctx* c = sh->ctx;
   DeviceGuard g;
   const int nl = (int)c->local.size();
+  ctx_fence(c);       // every rank has left its previous matvec: halos and send buffers may be written again
   ed_dvec *u_cur = nullptr, *u_prev = nullptr, *w = nullptr;
   auto mk = [&](ed_dvec** v) { const int rc = ed_dvec_create(sh, v); ED_REQUIRE(rc == ED_OK, rc, ed_last_error()); };
   mk(&u_cur); mk(&u_prev); mk(&w);
@@ -953,6 +1145,7 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
     norms[0].download(hn.data(), hn.size());
   }
   ctx_sync(c);
+  check_wait_error(sh);
   const int done = ed_lanczos_finish(hd.data(), hn.data(), n_steps, alpha, beta, ritz, n_ritz);
   if (steps_done) *steps_done = done;
   ED_CATCH

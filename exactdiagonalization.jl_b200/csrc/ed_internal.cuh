@@ -326,6 +326,7 @@ void ed_u1_suggest_rows(ed_oprep* o, int dtype, int world, int rank, int64_t* lo
 // ---- sharded tiled matvec (apply_u1.cu; driven by ctx.cu) -----------------------------------------------------------
 struct U1Pull { int peer; int chunk; int64_t src_off, dst_off, len; };   // elements: peer's SEND buffer -> this rank's halo
 struct U1Pack { int64_t src_off, dst_off, len; };                        // elements: this rank's x -> its send buffer
+struct U1Push { int recv; int chunk; int64_t src_off, dst_off, len; };   // elements: this rank's x -> rank recv's halo
 struct U1ShardLayout {
   int world = 1, rank = 0, n_chunks = 1;
   int64_t n_local = 0, n_halo = 0, n_send = 0; // elements
@@ -333,7 +334,9 @@ struct U1ShardLayout {
   std::vector<int64_t> range_lo, range_hi;     // global row ranges owned by this rank, ascending; local order = this order
   std::vector<uint32_t> tile_H;                // this rank's tiles in launch order
   std::vector<int64_t> tile_off;               // their offsets in the local vectors (storage is ascending in H)
-  std::vector<U1Pack> packs;                   // what this rank gathers into its send buffer for its peers
+  std::vector<U1Pack> packs;                   // what this rank gathers into its send buffer for its peers (pull exchange)
+  std::vector<U1Push> pushes;                  // the same tiles written straight into the peers' halos (push exchange), by chunk
+  std::vector<int64_t> chunk_halo_rows;        // [n_chunks] rows of this rank's halo that launch chunk c waits for
   std::vector<int> chunk_first;                // [n_chunks + 1] positions in tile_H
   std::vector<int64_t> dir;                    // [2^hb] see U1Params::dir
   std::vector<U1Pull> pulls;                   // ordered by chunk, one per (chunk, peer)

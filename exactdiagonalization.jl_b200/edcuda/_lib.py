@@ -144,7 +144,7 @@ SIGNATURES = {
     "ed_apply_sharded": (C.c_int, [vp, vp, vp, i32, vp]),
     "ed_sharded_profile": (C.c_int, [vp, vp, vp, vp]),
     "ed_lanczos_sharded": (C.c_int, [vp, i32, u64, vp, vp, vp, vp, i32, P(i32), P(dbl)]),
-    "ed_shard_plan_describe": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "ed_shard_plan_describe": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -310,13 +310,16 @@ int ed_ctx_allreduce_host(ed_ctx* ctx, double* values, int32_t count, int32_t op
 
 /* opreps[i] = the representation created on local rank i's device (same operator and basis everywhere).
  * exchange: 0 = automatic, 1 = NCCL all-gather of x per matvec (contiguous row ranges; any representation),
- *           2 = halo copies (tiled U(1) kernel only): every rank owns whole kernel tiles, the peer tiles it reads are
- *               copied by the copy engines over NVLink into a compact halo buffer in n_chunks pieces, each kernel chunk
- *               waiting only for its own piece.  Automatic = 2 where supported.  n_chunks <= 0: default (8). */
+ *           2, 3 = halo exchange (tiled U(1) kernel only): every rank owns whole kernel tiles; the peer tiles it reads land
+ *               in a compact halo buffer, piece by piece in the order its n_chunks launch chunks need them, each chunk
+ *               waiting only for its own piece.  3 (automatic where supported): the OWNER writes them with remote
+ *               stores over NVLink and bumps an arrival counter per chunk; 2: the owner packs a send buffer and the
+ *               reader's copy engines pull it.  n_chunks <= 0: default (8). */
 int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32_t exchange, int32_t n_chunks, ed_sharded** out);
 int ed_sharded_destroy(ed_sharded* sh);
 /* rows owned by local rank `local_index`, elements it copies from peers per matvec, number of its global row ranges,
- * peer copies and launch chunks per matvec, and whether the halo exchange is in use.  Outputs may be NULL. */
+ * peer copies (pull) or pushed pieces (push) and launch chunks per matvec, and the exchange in use: 0 all-gather,
+ * 1 halo by pulls, 2 halo by pushes.  Outputs may be NULL. */
 int ed_sharded_info(const ed_sharded* sh, int32_t local_index, int64_t* n_local, int64_t* n_halo, int32_t* n_ranges,
                     int32_t* n_pulls, int32_t* n_chunks, int32_t* halo_exchange);
 /* the global row ranges [row_lo[k], row_hi[k]) of that rank, ascending; its local vectors store them back to back. */
@@ -348,15 +351,16 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
 /* Host-only description (no GPU needed) of rank `rank`'s share of the halo-exchange layout for operator `op` on the
  * n_set-particle sector of n_bits spin-1/2 sites (policy 0 = planner's choice, 1 = ascending row ranges, 2 = wrap-aware
  * ranges, 3 = best popcount ordering).
- * counts[10] = {rows, halo rows, ranges, tiles, pulls, reads, chunks, dim, packs, send rows}.
+ * counts[12] = {rows, halo rows, ranges, tiles, pulls, reads, chunks, dim, packs, send rows, pushes, 0}.
  * Optional outputs (NULL to skip): ranges[2*ranges] = (lo, hi);
  * tiles[4*tiles] = (global first row, rows, local offset, launch chunk), in launch order;
  * pulls[5*pulls] = (peer, chunk, offset in the PEER'S SEND BUFFER, offset in the halo, rows);
  * packs[3*packs] = (offset in this rank's vector, offset in its send buffer, rows);
- * reads[4*reads] = (tile index, global first row of the tile it reads, rows, where: offset | 1<<62 if in the halo). */
+ * reads[4*reads] = (tile index, global first row of the tile it reads, rows, where: offset | 1<<62 if in the halo);
+ * pushes[5*pushes] = (receiver, its launch chunk, offset in this rank's vector, offset in the RECEIVER'S halo, rows). */
 int ed_shard_plan_describe(const ed_operator* op, int32_t n_bits, int32_t n_set, int32_t dtype, int32_t world, int32_t rank,
                            int32_t n_chunks, int32_t policy, int64_t* counts, int64_t* ranges, int64_t* tiles,
-                           int64_t* pulls, int64_t* packs, int64_t* reads);
+                           int64_t* pulls, int64_t* packs, int64_t* reads, int64_t* pushes);
 
 #ifdef __cplusplus
 }

@@ -39,19 +39,20 @@ def _terms(n, model):
 def describe(ed, terms, n, n_dn, world, rank, n_chunks=4, policy=0, dtype=0):
     from edcuda._lib import lib, check
     op = ed.Operator([(int(m), int(r), int(c), float(a)) for m, r, c, a in zip(*terms)])
-    counts = (C.c_int64 * 10)()
+    counts = (C.c_int64 * 12)()
     args = (op.handle(), n, n_dn, dtype, world, rank, n_chunks, policy)
-    check(lib.ed_shard_plan_describe(*args, counts, None, None, None, None, None))
-    n_local, n_halo, n_ranges, n_tiles, n_pulls, n_reads, chunks, dim, n_packs, n_send = list(counts)
+    check(lib.ed_shard_plan_describe(*args, counts, None, None, None, None, None, None))
+    n_local, n_halo, n_ranges, n_tiles, n_pulls, n_reads, chunks, dim, n_packs, n_send, n_pushes, _ = list(counts)
+    pushes = np.zeros((max(n_pushes, 1), 5), dtype=np.int64)
     ranges = np.zeros((max(n_ranges, 1), 2), dtype=np.int64)
     tiles = np.zeros((max(n_tiles, 1), 4), dtype=np.int64)
     pulls = np.zeros((max(n_pulls, 1), 5), dtype=np.int64)
     packs = np.zeros((max(n_packs, 1), 3), dtype=np.int64)
     reads = np.zeros((max(n_reads, 1), 4), dtype=np.int64)
     check(lib.ed_shard_plan_describe(*args, counts, ranges.ctypes.data, tiles.ctypes.data, pulls.ctypes.data, packs.ctypes.data,
-                                     reads.ctypes.data))
+                                     reads.ctypes.data, pushes.ctypes.data))
     return dict(n_local=n_local, n_halo=n_halo, n_send=n_send, dim=dim, chunks=chunks, ranges=ranges[:n_ranges], tiles=tiles[:n_tiles],
-                pulls=pulls[:n_pulls], packs=packs[:n_packs], reads=reads[:n_reads])
+                pulls=pulls[:n_pulls], packs=packs[:n_packs], reads=reads[:n_reads], pushes=pushes[:n_pushes])
 
 
 def send_buffer(plan, u_local):
@@ -104,6 +105,17 @@ def test_plans_replayed_on_numpy(ed, n, n_dn, model, world, chunks, policy):
             ready[dst:dst + ln] = chunk
         assert not np.isnan(halo).any()                             # the pulls fill the halo completely, nothing twice
         assert sum(pl[4] for pl in p["pulls"]) == p["n_halo"]
+        # push exchange: the peers write the same tiles straight into this rank's halo, earliest chunk first
+        halo2 = np.full(p["n_halo"], np.nan)
+        ready2 = np.full(p["n_halo"], 1 << 30, dtype=np.int64)
+        for s_rank, q in enumerate(plans):
+            assert np.all(np.diff(q["pushes"][:, 1]) >= 0)
+            for recv, chunk, src, dst, ln in q["pushes"]:
+                if recv == r:
+                    assert s_rank != r and np.isnan(halo2[dst:dst + ln]).all()
+                    halo2[dst:dst + ln] = local[s_rank][src:src + ln]
+                    ready2[dst:dst + ln] = chunk
+        assert np.array_equal(halo2, halo) and np.array_equal(ready2, ready)
         for ti, gbase, size, where in p["reads"]:
             assert where >= 0
             if where & HALO:
@@ -125,8 +137,8 @@ def test_describe_rejects_unsupported(ed):
     from edcuda._lib import lib
     hs, pauli = ed.spin_half_system(8)
     op = ed.simplify(pauli(0, "x") * pauli(1, "x") * pauli(2, "x"))      # three-site term: not a bond Hamiltonian
-    counts = (C.c_int64 * 10)()
-    assert lib.ed_shard_plan_describe(op.handle(), 8, 4, 0, 2, 0, 2, 0, counts, None, None, None, None, None) == ed._lib.ED_ERR_UNSUPPORTED
+    counts = (C.c_int64 * 12)()
+    assert lib.ed_shard_plan_describe(op.handle(), 8, 4, 0, 2, 0, 2, 0, counts, None, None, None, None, None, None) == ed._lib.ED_ERR_UNSUPPORTED
 
 
 # ------------------------------------------------------------------ world-2 gloo run

@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--impl", default="edcuda")
     ap.add_argument("--workload", default="xxz_chain_L32_sz0")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "push", "pull", "allgather"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "push", "pull", "cepush", "allgather"],
                     help="N>1: how remote rows of x reach a rank: halo copies over NVLink (packed by the owner, pulled by copy engines) or an NCCL all-gather per matvec")
     ap.add_argument("--chunks", type=int, default=0, help="N>1: launch chunks per matvec (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -461,8 +461,9 @@ def main():
         phases = sh.profile(yv, xv) if info["exchange"] == "halo" else None
         details.update({"rows_per_gpu": n_local, "sharding": "tiles assigned by the library's planner (ed_u1_shard_layout)" if info["exchange"] == "halo" else "contiguous row ranges",
                         "exchange": ("halo exchange over NVLink (%s), interior tiles first, %d launch chunks, one NCCL fence per matvec" % (
-                                     "owners write the tiles their peers read into the peers' halo buffers with remote stores and bump a per-chunk arrival counter"
-                                     if info["halo_transport"] == "owner pushes" else "owner-side pack + copy-engine pulls of the packed tiles", info["n_chunks"]))
+                                     {"owner pushes": "owners write the tiles their peers read into the peers' halo buffers with remote stores and bump a per-chunk arrival counter",
+                                      "owner copy-engine pushes": "owner-side pack, the owner's copy engines write the pieces into the peers' halo buffers, per-chunk arrival counters",
+                                      "copy-engine pulls": "owner-side pack + reader-side copy-engine pulls of the packed tiles"}[info["halo_transport"]], info["n_chunks"]))
                         if info["exchange"] == "halo" else "NCCL all-gather of x per matvec", "halo_rows_max": halo_max,
                         "nvlink_bytes_per_rank_per_matvec_max": halo_max * 8, "pulls_per_matvec": info["n_pulls"],
                         "phases_run_back_to_back_ms": phases,

@@ -1322,7 +1322,13 @@ void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunk
       at += len;
     }
   }
+  // the same as contiguous pieces of the packed send buffer (copy-engine push): one per (receiver, chunk)
+  for (const U1Push& p : S.pushes) {
+    if (!S.piece_pushes.empty() && S.piece_pushes.back().recv == p.recv && S.piece_pushes.back().chunk == p.chunk) S.piece_pushes.back().len += p.len;
+    else S.piece_pushes.push_back({p.recv, p.chunk, G.send_off(rank, p.recv, p.chunk), p.dst_off, p.len});
+  }
   std::stable_sort(S.pushes.begin(), S.pushes.end(), [](const U1Push& a, const U1Push& b) { return a.chunk < b.chunk; });
+  std::stable_sort(S.piece_pushes.begin(), S.piece_pushes.end(), [](const U1Push& a, const U1Push& b) { return a.chunk < b.chunk; });
   // packs: for every receiver (ascending) and chunk, its halo tiles owned by this rank, in its halo order
   int64_t send = 0;
   for (int r = 0; r < world; ++r) {

@@ -248,6 +248,7 @@ struct ShardRank {
   void* halo_mem = nullptr;
   unsigned long long* counters = nullptr;        // [n_chunks] rows that have arrived for each chunk, cumulative over matvecs
   std::vector<void*> peer_halo;                  // [world]
+  std::vector<unsigned long long*> peer_counters; // [world] the peers' arrival counters (behind their halos)
   DevBuf<int64_t> d_push;                        // [4 * n_push_items] (src offset, destination address, rows, counter address)
   int n_push_items = 0;
   unsigned long long seq = 0;                    // matvecs pushed so far
@@ -265,7 +266,9 @@ struct ed_sharded {
   ed_ctx* ctx = nullptr;
   int dtype = ED_F64;
   bool halo = false;
-  bool push = false;                         // halo exchange by owner-side pushes (remote stores + arrival counters)
+  bool push = false;                         // halo exchange by owner-side pushes (arrival counters) instead of reader-side pulls
+  bool ce_push = false;                      // ... pushed by the owner's copy engines from a packed send buffer instead of by SM stores
+  int push_ctas = 64;                        // grid of the (persistent) push kernel: a few SMs' worth, the rest keep computing
   int64_t dim = 0;
   size_t es = 8;
   std::vector<ShardRank> r;                  // per local rank
@@ -288,15 +291,31 @@ struct ed_dvec {
 // stream waits (k_wait_rows) until the counter has reached seq * (rows the chunk needs): everything this kernel and the
 // kernels behind the wait need is ordered by fence + atomic on the sender and by the kernel boundary on the receiver.
 template <typename VecT>
-__global__ void __launch_bounds__(256) k_push(const VecT* __restrict__ x, const int64_t* __restrict__ items) {
-  const int64_t* it = items + 4 * (int64_t)blockIdx.x;
-  const VecT* src = x + it[0];
-  VecT* dst = reinterpret_cast<VecT*>(it[1]);
-  const int len = (int)it[2];
-  for (int i = threadIdx.x; i < len; i += 256) dst[i] = src[i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd_system(reinterpret_cast<unsigned long long*>(it[3]), (unsigned long long)len);
+__global__ void __launch_bounds__(256) k_push(const VecT* __restrict__ x, const int64_t* __restrict__ items, int n_items) {
+  // persistent: a small grid walks the item list (earliest chunk first) so that the compute kernels keep most SMs
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int64_t* it = items + 4 * (int64_t)item;
+    const VecT* src = x + it[0];
+    VecT* dst = reinterpret_cast<VecT*>(it[1]);
+    const int len = (int)it[2];
+    int i = threadIdx.x;
+    for (; i + 7 * 256 < len; i += 8 * 256) {          // eight independent loads in flight per thread
+      VecT v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[i + u * 256];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[i + u * 256] = v[u];
+    }
+    for (; i < len; i += 256) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd_system(reinterpret_cast<unsigned long long*>(it[3]), (unsigned long long)len);
+  }
+}
+
+// copy-engine push: the arrival counter is bumped by a one-thread kernel queued behind the copy
+__global__ void k_signal_rows(unsigned long long* counter, unsigned long long rows) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { __threadfence_system(); atomicAdd_system(counter, rows); }
 }
 
 // one thread polls the arrival counter of a launch chunk; gives up after ~20 s (sets *err) instead of hanging the GPU
@@ -329,18 +348,29 @@ void sharded_pack(ed_sharded* S, ed_dvec* x) {
   ed_ctx* c = S->ctx;
   if (S->push) {
     // x of every rank is final at this point of its main stream, and every peer is done with its previous halo (a
-    // collective ran after its last kernel): start writing the peers' halos on the high-priority stream
+    // collective ran after its last kernel): start filling the peers' halos on the high-priority stream
     for (size_t i = 0; i < c->local.size(); ++i) {
       CtxRank& R = c->local[i];
       ShardRank& Q = S->r[i];
       ++Q.seq;
-      if (!Q.n_push_items) continue;
+      if (Q.L.pushes.empty()) continue;
       ED_CUDA(cudaSetDevice(R.device));
       ED_CUDA(cudaEventRecord(R.ev, R.stream));
       ED_CUDA(cudaStreamWaitEvent(R.push, R.ev, 0));
       ed_push_stream(R.push);
-      if (S->dtype == ED_F64) ED_LAUNCH(k_push<double>, Q.n_push_items, 256, 0, reinterpret_cast<const double*>(x->local[i]), Q.d_push.p);
-      else ED_LAUNCH(k_push<double2>, Q.n_push_items, 256, 0, reinterpret_cast<const double2*>(x->local[i]), Q.d_push.p);
+      if (!S->ce_push) {
+        const int grid = std::min(Q.n_push_items, S->push_ctas);
+        if (S->dtype == ED_F64) ED_LAUNCH(k_push<double>, grid, 256, 0, reinterpret_cast<const double*>(x->local[i]), Q.d_push.p, Q.n_push_items);
+        else ED_LAUNCH(k_push<double2>, grid, 256, 0, reinterpret_cast<const double2*>(x->local[i]), Q.d_push.p, Q.n_push_items);
+      } else {
+        if (S->dtype == ED_F64) ED_LAUNCH(k_pack<double>, Q.n_pack_items, 256, 0, reinterpret_cast<const double*>(x->local[i]), reinterpret_cast<double*>(Q.send[0]), Q.d_packs.p);
+        else ED_LAUNCH(k_pack<double2>, Q.n_pack_items, 256, 0, reinterpret_cast<const double2*>(x->local[i]), reinterpret_cast<double2*>(Q.send[0]), Q.d_packs.p);
+        for (const U1Push& p : Q.L.piece_pushes) {
+          ED_CUDA(cudaMemcpyAsync(static_cast<char*>(Q.peer_halo[p.recv]) + (size_t)p.dst_off * S->es, static_cast<const char*>(Q.send[0]) + (size_t)p.src_off * S->es,
+                                  (size_t)p.len * S->es, cudaMemcpyDeviceToDevice, R.push));
+          ED_LAUNCH(k_signal_rows, 1, 32, 0, Q.peer_counters[p.recv] + p.chunk, (unsigned long long)p.len);
+        }
+      }
       ed_pop_stream();
     }
     return;
@@ -663,7 +693,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   ED_TRY
   ED_REQUIRE(ctx && opreps && out, ED_ERR_ARGUMENT, "null argument");
   ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
-  ED_REQUIRE(exchange >= 0 && exchange <= 3, ED_ERR_ARGUMENT, "exchange: 0 automatic, 1 NCCL all-gather, 2 halo by copy-engine pulls, 3 halo by owner pushes");
+  ED_REQUIRE(exchange >= 0 && exchange <= 4, ED_ERR_ARGUMENT, "exchange: 0 automatic, 1 NCCL all-gather, 2 halo by copy-engine pulls, 3 halo by owner SM pushes, 4 halo by owner copy-engine pushes");
   DeviceGuard g;
   std::unique_ptr<ed_sharded> S(new ed_sharded());
   S->ctx = ctx;
@@ -686,7 +716,14 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   }
   ED_REQUIRE(exchange < 2 || fast, ED_ERR_UNSUPPORTED, "the halo exchange is defined for the tiled U(1) kernel only");
   S->halo = fast && exchange != 1;
-  S->push = S->halo && exchange != 2 && !getenv("EDCUDA_SHARD_PULL");
+  // transport of the halo: 2 = reader-side copy-engine pulls, 3 = owner-side SM pushes, 4 = owner-side copy-engine pushes;
+  // automatic: EDCUDA_SHARD_TRANSPORT (pull | push | cepush), default pull
+  int transport = exchange >= 2 ? exchange : 2;
+  if (exchange == 0)
+    if (const char* e = getenv("EDCUDA_SHARD_TRANSPORT")) transport = !strcmp(e, "push") ? 3 : !strcmp(e, "cepush") ? 4 : 2;
+  S->push = S->halo && transport >= 3;
+  S->ce_push = S->halo && transport == 4;
+  if (const char* e = getenv("EDCUDA_PUSH_CTAS")) S->push_ctas = std::max(1, atoi(e));
   S->rows_of_rank.assign(ctx->world, 0);
   for (int i = 0; i < nl; ++i) {
     CtxRank& R = ctx->local[i];
@@ -710,11 +747,12 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
         ED_CUDA(cudaMalloc(&Q.halo_mem, halo_bytes + (size_t)Q.L.n_chunks * sizeof(unsigned long long)));
         Q.counters = reinterpret_cast<unsigned long long*>(static_cast<char*>(Q.halo_mem) + halo_bytes);
         ED_CUDA(cudaMemsetAsync(Q.counters, 0, (size_t)Q.L.n_chunks * sizeof(unsigned long long), R.stream));
+        if (S->ce_push) ED_CUDA(cudaMalloc(&Q.send[0], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
       } else {
         Q.halo.alloc((size_t)std::max<int64_t>(Q.L.n_halo, 1) * S->es);
         for (int b = 0; b < 2; ++b) ED_CUDA(cudaMalloc(&Q.send[b], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
       }
-      if (!S->push) {
+      if (!S->push || S->ce_push) {
         std::vector<int64_t> items;
         for (const U1Pack& p : Q.L.packs)
           for (int64_t o = 0; o < p.len; o += PACK_ITEM) { items.push_back(p.src_off + o); items.push_back(p.dst_off + o); items.push_back(std::min<int64_t>(PACK_ITEM, p.len - o)); }
@@ -806,6 +844,9 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
       Q.n_push_items = (int)(items.size() / 4);
       if (items.empty()) items.assign(4, 0);
       Q.d_push.upload(items);
+      Q.peer_counters.assign(ctx->world, nullptr);
+      for (int r = 0; r < ctx->world; ++r)
+        Q.peer_counters[r] = reinterpret_cast<unsigned long long*>(static_cast<char*>(Q.peer_halo[r]) + halo_bytes_of[r]);
       ED_CUDA(cudaStreamSynchronize(ctx->local[i].stream));
     }
     ctx_fence(ctx);        // every rank's counters are zeroed before anyone pushes
@@ -862,7 +903,7 @@ int ed_sharded_info(const ed_sharded* sh, int32_t local_index, int64_t* n_local,
   if (n_ranges) *n_ranges = (int32_t)Q.range_lo.size();
   if (n_pulls) *n_pulls = sh->halo ? (int32_t)(sh->push ? Q.L.pushes.size() : Q.L.pulls.size()) : 0;
   if (n_chunks) *n_chunks = sh->halo ? Q.L.n_chunks : 1;
-  if (halo_exchange) *halo_exchange = sh->halo ? (sh->push ? 2 : 1) : 0;
+  if (halo_exchange) *halo_exchange = sh->halo ? (sh->ce_push ? 3 : sh->push ? 2 : 1) : 0;
   ED_CATCH
 }
 

@@ -336,6 +336,7 @@ struct U1ShardLayout {
   std::vector<int64_t> tile_off;               // their offsets in the local vectors (storage is ascending in H)
   std::vector<U1Pack> packs;                   // what this rank gathers into its send buffer for its peers (pull exchange)
   std::vector<U1Push> pushes;                  // the same tiles written straight into the peers' halos (push exchange), by chunk
+  std::vector<U1Push> piece_pushes;            // one contiguous piece per (receiver, chunk): src_off is in this rank's SEND buffer
   std::vector<int64_t> chunk_halo_rows;        // [n_chunks] rows of this rank's halo that launch chunk c waits for
   std::vector<int> chunk_first;                // [n_chunks + 1] positions in tile_H
   std::vector<int64_t> dir;                    // [2^hb] see U1Params::dir

@@ -259,6 +259,10 @@ k6b_canonicalize_nk(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict_
   int32_t* s_inv = reinterpret_cast<int32_t*>(s_lut + 2 * CB * NCH * 64);   // [2][CB * n1 * n2]
   uint64_t* s_mlo = reinterpret_cast<uint64_t*>(s_inv + 2 * CB * n1 * n2 + ((2 * CB * n1 * n2) & 1));   // [8] columns x < a of every row
   uint16_t* s_row = reinterpret_cast<uint16_t*>(s_mlo + 8);                 // [2^n1] (minimal rotation << 8) | shifts reaching it
+  // rows taken two at a time where that fits (2 n1 <= 12 bits, even n2): [2^(2 n1)] min of the two minimal rotations --
+  // half the look-ups of the scan that every (word, coset) pays; the rare candidate path still uses s_row
+  const bool pairs = (2 * n1 <= 12) && (n2 % 2 == 0);
+  uint16_t* s_pair = s_row + (1 << n1);                                     // (min of the two << 8) | which of the two rows attain it
   const int nt = n1 * n2;
   const int tid = threadIdx.x;
   const uint64_t full = n_bits >= 64 ? ~0ull : ((1ull << n_bits) - 1ull);
@@ -276,6 +280,14 @@ k6b_canonicalize_nk(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict_
     uint64_t m = 0;
     for (int y = 0; y < n2; ++y) m |= (uint64_t)((1u << tid) - 1u) << (n1 * y);
     s_mlo[tid] = tid <= n1 ? (m & full) : 0ull;
+  }
+  if (pairs) {
+    __syncthreads();
+    for (int v = tid; v < (1 << (2 * n1)); v += 256) {
+      const uint32_t lo = (uint32_t)s_row[v & rmask] >> 8, hi = (uint32_t)s_row[(v >> n1) & rmask] >> 8;
+      const uint32_t mn = min(lo, hi);
+      s_pair[v] = (uint16_t)((mn << 8) | (lo == mn ? 1u : 0u) | (hi == mn ? 2u : 0u));
+    }
   }
   const int64_t base = (int64_t)blockIdx.x * (256 * W);
   uint64_t w[W], best[W];
@@ -311,7 +323,7 @@ k6b_canonicalize_nk(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict_
       const uint64_t* L = s_lut + ((size_t)buf * CB + ji) * NCH * 64;
       const int32_t* inv_tab = s_inv + ((size_t)buf * CB + ji) * nt;
       uint64_t im[W];
-      uint32_t m[W];
+      uint32_t m[W], rows[W];     // row minimum of the image and the set of rows that attain it
       bool cand = false;
 #pragma unroll
       for (int k = 0; k < W; ++k) {
@@ -319,23 +331,39 @@ k6b_canonicalize_nk(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict_
 #pragma unroll
         for (int c = 0; c < NCH; ++c) v |= L[off[k][c]];
         im[k] = v;
-        uint32_t mm = 0xFFu;
+        uint32_t mm = 0xFFu, rr = 0u;
+        if (pairs) {
+          const uint32_t pmask = (1u << (2 * n1)) - 1u;
+#pragma unroll(FIXED ? N2 / 2 : 1)
+          for (int y = 0; y < n2; y += 2) {
+            const uint32_t t = s_pair[(uint32_t)(v >> (n1 * y)) & pmask];
+            const uint32_t tm = t >> 8;
+            rr = tm < mm ? ((t & 3u) << y) : (tm == mm ? (rr | ((t & 3u) << y)) : rr);
+            mm = min(mm, tm);
+          }
+        } else {
 #pragma unroll(FIXED ? N2 : 1)
-        for (int y = 0; y < n2; ++y) mm = min(mm, (uint32_t)s_row[(uint32_t)(v >> (n1 * y)) & rmask] >> 8);
+          for (int y = 0; y < n2; ++y) {
+            const uint32_t tm = (uint32_t)s_row[(uint32_t)(v >> (n1 * y)) & rmask] >> 8;
+            rr = tm < mm ? (1u << y) : (tm == mm ? (rr | (1u << y)) : rr);
+            mm = min(mm, tm);
+          }
+        }
         m[k] = mm;
+        rows[k] = rr;
         cand |= mm <= (uint32_t)(best[k] >> top_shift);
       }
       if (__any_sync(0xffffffffu, cand)) {            // warp-uniform branch: most cosets cannot beat the best word so far
 #pragma unroll
         for (int k = 0; k < W; ++k) {
-          if (m[k] > (uint32_t)(best[k] >> top_shift)) continue;
-          for (int y = 0; y < n2; ++y) {
-            const uint32_t t = s_row[(uint32_t)(im[k] >> (n1 * y)) & rmask];
-            if ((t >> 8) != m[k]) continue;
+          uint32_t rr = m[k] <= (uint32_t)(best[k] >> top_shift) ? rows[k] : 0u;
+          while (rr) {                                // usually one row
+            const int y = __ffs(rr) - 1;
+            rr &= rr - 1u;
             const int b = n2 - 1 - y;                  // Ty^b brings row y to the top
             const uint64_t ub = b ? (((im[k] << (n1 * b)) | (im[k] >> (n_bits - n1 * b))) & full) : im[k];
-            uint32_t shifts = t & 0xFFu;
-            while (shifts) {
+            uint32_t shifts = (uint32_t)s_row[(uint32_t)(im[k] >> (n1 * y)) & rmask] & 0xFFu;
+            while (shifts) {                          // usually one shift
               const int a = __ffs(shifts) - 1;
               shifts &= shifts - 1u;
               const uint64_t mlo = s_mlo[a];
@@ -527,7 +555,8 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
       const int grid_n = (int)((n_hits + 511) / 512);
 #define ED_K6NK(NCH_, N1_, N2_)                                                                                              \
       do {                                                                                                                   \
-        const size_t smem_n = (size_t)2 * 4 * NCH_ * 64 * 8 + (size_t)(2 * 4 * nt_ + ((2 * 4 * nt_) & 1)) * 4 + 8 * 8 + ((size_t)2 << sd.tr_n1); \
+        const size_t smem_n = (size_t)2 * 4 * NCH_ * 64 * 8 + (size_t)(2 * 4 * nt_ + ((2 * 4 * nt_) & 1)) * 4 + 8 * 8 + ((size_t)2 << sd.tr_n1) + \
+                              ((2 * sd.tr_n1 <= 12 && sd.tr_n2 % 2 == 0) ? ((size_t)2 << (2 * sd.tr_n1)) : 0); \
         ED_LAUNCH((k6b_canonicalize_nk<NCH_, N1_, N2_>), grid_n, 256, smem_n, sd.tr_ncos, sd.tr_n1, sd.tr_n2, sd.tr_lut6.p, \
                   sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);                                                               \
       } while (0)

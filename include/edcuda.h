@@ -310,16 +310,17 @@ int ed_ctx_allreduce_host(ed_ctx* ctx, double* values, int32_t count, int32_t op
 
 /* opreps[i] = the representation created on local rank i's device (same operator and basis everywhere).
  * exchange: 0 = automatic, 1 = NCCL all-gather of x per matvec (contiguous row ranges; any representation),
- *           2, 3 = halo exchange (tiled U(1) kernel only): every rank owns whole kernel tiles; the peer tiles it reads land
- *               in a compact halo buffer, piece by piece in the order its n_chunks launch chunks need them, each chunk
- *               waiting only for its own piece.  3 (automatic where supported): the OWNER writes them with remote
- *               stores over NVLink and bumps an arrival counter per chunk; 2: the owner packs a send buffer and the
- *               reader's copy engines pull it.  n_chunks <= 0: default (8). */
+ *           2, 3, 4 = halo exchange (tiled U(1) kernel only): every rank owns whole kernel tiles; the peer tiles it reads
+ *               land in a compact halo buffer, piece by piece in the order its n_chunks launch chunks need them, each
+ *               chunk waiting only for its own piece.  2: the owner packs a send buffer and the READER's copy engines pull
+ *               it; 3: the OWNER writes the tiles with remote stores from a small persistent kernel and bumps a per-chunk
+ *               arrival counter (remote atomic); 4: the owner packs and its copy engines push.  Automatic = halo where
+ *               supported (transport: EDCUDA_SHARD_TRANSPORT = pull | push | cepush, default pull).  n_chunks <= 0: 8. */
 int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32_t exchange, int32_t n_chunks, ed_sharded** out);
 int ed_sharded_destroy(ed_sharded* sh);
 /* rows owned by local rank `local_index`, elements it copies from peers per matvec, number of its global row ranges,
  * peer copies (pull) or pushed pieces (push) and launch chunks per matvec, and the exchange in use: 0 all-gather,
- * 1 halo by pulls, 2 halo by pushes.  Outputs may be NULL. */
+ * 1 halo by pulls, 2 halo by SM pushes, 3 halo by copy-engine pushes.  Outputs may be NULL. */
 int ed_sharded_info(const ed_sharded* sh, int32_t local_index, int64_t* n_local, int64_t* n_halo, int32_t* n_ranges,
                     int32_t* n_pulls, int32_t* n_chunks, int32_t* halo_exchange);
 /* the global row ranges [row_lo[k], row_hi[k]) of that rank, ascending; its local vectors store them back to back. */

@@ -87,19 +87,20 @@ def _check_sharded(ed, ctx, n, n_dn, model, exchange="auto", n_chunks=0, cplx=Fa
     return out
 
 
-@pytest.mark.parametrize("transport", ["push", "pull"])
+@pytest.mark.parametrize("transport", ["pull", "push", "cepush"])
 @pytest.mark.parametrize("n,n_dn,model,world,chunks", [(20, 10, "xxz", 2, 0), (22, 11, "xxz", 4, 3), (20, 7, "j1j2", 3, 2),
                                                        (18, 9, "open", 2, 1), (24, 12, "xxz", 8, 8), (16, 8, "square", 4, 4)])
 def test_loopback_halo_exchange_vs_c_oracle(gpu_ed, n, n_dn, model, world, chunks, transport):
-    """world ranks on one GPU: planner's partition, interior tiles first, halo filled chunk by chunk -- by the owners'
-    remote stores + arrival counters (push, the default) or by owner-side packing + copy-engine pulls."""
+    """world ranks on one GPU: planner's partition, interior tiles first, halo filled chunk by chunk -- by owner-side
+    packing + reader-side copy-engine pulls, by the owners' remote stores + arrival counters (push), or by the owners'
+    copy engines (cepush)."""
     ed = gpu_ed
     from edcuda.distributed import Context
     ctx = Context.single_process([0] * world)
     assert ctx.world == world and ctx.n_local == world and ctx.nccl_version == 0
     out = _check_sharded(ed, ctx, n, n_dn, model, n_chunks=chunks, exchange=transport)
     assert out["info"]["exchange"] == "halo"
-    assert out["info"]["halo_transport"] == ("owner pushes" if transport == "push" else "copy-engine pulls")
+    assert out["info"]["halo_transport"] == {"pull": "copy-engine pulls", "push": "owner pushes", "cepush": "owner copy-engine pushes"}[transport]
     ctx.close()
 
 
@@ -196,8 +197,9 @@ def test_nccl_single_process_context(gpu_ed):
     ctx = Context.single_process(list(range(n_gpu)))
     assert ctx.nccl_version > 0
     out = _check_sharded(ed, ctx, 24, 12, "xxz", lanczos_steps=60)
-    assert out["info"]["exchange"] == "halo" and out["info"]["halo_transport"] == "owner pushes"
-    _check_sharded(ed, ctx, 22, 11, "xxz", exchange="pull", lanczos_steps=20)
+    assert out["info"]["exchange"] == "halo"
+    _check_sharded(ed, ctx, 22, 11, "xxz", exchange="push", lanczos_steps=20)
+    _check_sharded(ed, ctx, 22, 11, "xxz", exchange="cepush", lanczos_steps=20)
     _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
     ctx.close()
 
@@ -214,7 +216,8 @@ def _rank_worker(rank, world, port, q):
         ctx = Context.from_env()
         assert ctx.world == world and ctx.n_local == 1 and ctx.rank == rank
         out = _check_sharded(ed, ctx, 24, 12, "xxz", lanczos_steps=60)
-        _check_sharded(ed, ctx, 22, 11, "xxz", exchange="pull", lanczos_steps=20)
+        _check_sharded(ed, ctx, 22, 11, "xxz", exchange="push", lanczos_steps=20)
+        _check_sharded(ed, ctx, 22, 11, "xxz", exchange="cepush", lanczos_steps=20)
         _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
         ctx.barrier()
         ctx.close()

@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--impl", default="edcuda")
     ap.add_argument("--workload", default="xxz_chain_L32_sz0")
     ap.add_argument("--kernel", type=int, default=0, help="0 = automatic (fast path), 1 = generic term-walk kernel")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "push", "pull", "cepush", "allgather"],
+    ap.add_argument("--exchange", default="auto", choices=["auto", "halo", "push", "pull", "cepush", "nccl", "allgather"],
                     help="N>1: how remote rows of x reach a rank: halo copies over NVLink (packed by the owner, pulled by copy engines) or an NCCL all-gather per matvec")
     ap.add_argument("--chunks", type=int, default=0, help="N>1: launch chunks per matvec (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -463,6 +463,7 @@ def main():
                         "exchange": ("halo exchange over NVLink (%s), interior tiles first, %d launch chunks, one NCCL fence per matvec" % (
                                      {"owner pushes": "owners write the tiles their peers read into the peers' halo buffers with remote stores and bump a per-chunk arrival counter",
                                       "owner copy-engine pushes": "owner-side pack, the owner's copy engines write the pieces into the peers' halo buffers, per-chunk arrival counters",
+                                      "nccl send/recv": "owner-side pack, one grouped ncclSend/ncclRecv per launch chunk",
                                       "copy-engine pulls": "owner-side pack + reader-side copy-engine pulls of the packed tiles"}[info["halo_transport"]], info["n_chunks"]))
                         if info["exchange"] == "halo" else "NCCL all-gather of x per matvec", "halo_rows_max": halo_max,
                         "nvlink_bytes_per_rank_per_matvec_max": halo_max * 8, "pulls_per_matvec": info["n_pulls"],

@@ -40,6 +40,8 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -60,7 +62,7 @@ NcclApi& nccl() {
   ED_REQUIRE(api.name, ED_ERR_UNSUPPORTED, "libnccl lacks nccl" #name)
   ED_NCCL_SYM(GetVersion); ED_NCCL_SYM(GetUniqueId); ED_NCCL_SYM(CommInitRank); ED_NCCL_SYM(CommInitAll);
   ED_NCCL_SYM(CommDestroy); ED_NCCL_SYM(AllReduce); ED_NCCL_SYM(AllGather); ED_NCCL_SYM(Broadcast);
-  ED_NCCL_SYM(GroupStart); ED_NCCL_SYM(GroupEnd); ED_NCCL_SYM(GetErrorString);
+  ED_NCCL_SYM(GroupStart); ED_NCCL_SYM(GroupEnd); ED_NCCL_SYM(GetErrorString); ED_NCCL_SYM(Send); ED_NCCL_SYM(Recv);
 #undef ED_NCCL_SYM
   return api;
 }
@@ -268,6 +270,7 @@ struct ed_sharded {
   bool halo = false;
   bool push = false;                         // halo exchange by owner-side pushes (arrival counters) instead of reader-side pulls
   bool ce_push = false;                      // ... pushed by the owner's copy engines from a packed send buffer instead of by SM stores
+  bool nccl_p2p = false;                     // halo pieces moved by grouped ncclSend / ncclRecv (one group per launch chunk)
   int push_ctas = 64;                        // grid of the (persistent) push kernel: a few SMs' worth, the rest keep computing
   int64_t dim = 0;
   size_t es = 8;
@@ -346,6 +349,45 @@ namespace {
 void sharded_pack(ed_sharded* S, ed_dvec* x) {
   if (!S->halo || S->ctx->world == 1) return;
   ed_ctx* c = S->ctx;
+  if (S->nccl_p2p) {
+    // pack on the high-priority stream, then one ncclSend/ncclRecv group per launch chunk: the sends carry the pieces the
+    // peers' chunk c reads, the receives fill this rank's chunk-c part of the halo; an event per chunk releases the kernels.
+    // No fence: send/recv pairs synchronise the two ranks involved, the halo is guarded by the event recorded below.
+    NcclApi& N = nccl();
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = S->r[i];
+      ED_CUDA(cudaSetDevice(R.device));
+      ED_CUDA(cudaEventRecord(R.ev, R.stream));          // x final; this rank's kernels of the previous matvec done with the halo
+      ED_CUDA(cudaStreamWaitEvent(R.push, R.ev, 0));
+      if (Q.n_pack_items) {
+        ed_push_stream(R.push);
+        if (S->dtype == ED_F64) ED_LAUNCH(k_pack<double>, Q.n_pack_items, 256, 0, reinterpret_cast<const double*>(x->local[i]), reinterpret_cast<double*>(Q.send[0]), Q.d_packs.p);
+        else ED_LAUNCH(k_pack<double2>, Q.n_pack_items, 256, 0, reinterpret_cast<const double2*>(x->local[i]), reinterpret_cast<double2*>(Q.send[0]), Q.d_packs.p);
+        ed_pop_stream();
+      }
+    }
+    const size_t per = S->es / 8;      // doubles per element
+    const int n_chunks = S->r[0].L.n_chunks;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      ED_NCCL(N.GroupStart());
+      for (size_t i = 0; i < c->local.size(); ++i) {
+        CtxRank& R = c->local[i];
+        ShardRank& Q = S->r[i];
+        ED_CUDA(cudaSetDevice(R.device));
+        for (const U1Push& p : Q.L.piece_pushes)
+          if (p.chunk == ch) ED_NCCL(N.Send(static_cast<const char*>(Q.send[0]) + (size_t)p.src_off * S->es, (size_t)p.len * per, ncclDouble, p.recv, R.comm, R.push));
+        for (const U1Pull& p : Q.L.pulls)
+          if (p.chunk == ch) ED_NCCL(N.Recv(Q.halo.p + (size_t)p.dst_off * S->es, (size_t)p.len * per, ncclDouble, p.peer, R.comm, R.push));
+      }
+      ED_NCCL(N.GroupEnd());
+      for (size_t i = 0; i < c->local.size(); ++i) {
+        ED_CUDA(cudaSetDevice(c->local[i].device));
+        ED_CUDA(cudaEventRecord(S->r[i].ev_pull[(size_t)ch * ED_CTX_PULL_STREAMS], c->local[i].push));
+      }
+    }
+    return;
+  }
   if (S->push) {
     // x of every rank is final at this point of its main stream, and every peer is done with its previous halo (a
     // collective ran after its last kernel): start filling the peers' halos on the high-priority stream
@@ -389,7 +431,33 @@ void sharded_pack(ed_sharded* S, ed_dvec* x) {
 void sharded_apply(ed_sharded* S, ed_dvec* y, ed_dvec* x, bool packed, bool want_dot) {
   ed_ctx* c = S->ctx;
   DeviceGuard g;
-  if (S->halo && S->push) {
+  if (S->halo && S->nccl_p2p) {
+    if (!packed) sharded_pack(S, x);
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = S->r[i];
+      RankScope scope(R);
+      for (int ch = 0; ch < Q.L.n_chunks; ++ch) {
+        if (c->world > 1 && ch > 0) ED_CUDA(cudaStreamWaitEvent(R.stream, Q.ev_pull[(size_t)ch * ED_CTX_PULL_STREAMS], 0));
+        U1ShardLaunch A;
+        A.tile_H = Q.d_tile_H.p;
+        A.first = Q.L.chunk_first[ch];
+        A.count = Q.L.chunk_first[ch + 1] - Q.L.chunk_first[ch];
+        A.dir = Q.d_dir.p;
+        A.x_local = x->local[i];
+        A.x_halo = Q.halo.p;
+        A.y_local = y->local[i];
+        A.stream_mode = 0;
+        A.accumulate = 0;
+        A.partials = want_dot ? Q.partials.p : nullptr;
+        ed_apply_u1_sharded(Q.op, S->dtype, A);
+      }
+      if (want_dot) {
+        if (Q.L.tile_H.empty()) ED_CUDA(cudaMemsetAsync(Q.dot.p, 0, 2 * sizeof(double), R.stream));
+        else ed_reduce_pairs(Q.partials.p, (int)Q.L.tile_H.size(), Q.dot.p);
+      }
+    }
+  } else if (S->halo && S->push) {
     if (!packed) {
       ctx_fence(c);          // every rank is done with its previous halo and its x is final
       sharded_pack(S, x);
@@ -693,7 +761,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   ED_TRY
   ED_REQUIRE(ctx && opreps && out, ED_ERR_ARGUMENT, "null argument");
   ED_REQUIRE(dtype == ED_F64 || dtype == ED_C128, ED_ERR_ARGUMENT, "bad dtype");
-  ED_REQUIRE(exchange >= 0 && exchange <= 4, ED_ERR_ARGUMENT, "exchange: 0 automatic, 1 NCCL all-gather, 2 halo by copy-engine pulls, 3 halo by owner SM pushes, 4 halo by owner copy-engine pushes");
+  ED_REQUIRE(exchange >= 0 && exchange <= 5, ED_ERR_ARGUMENT, "exchange: 0 automatic, 1 NCCL all-gather, 2 halo by copy-engine pulls, 3 halo by owner SM pushes, 4 halo by owner copy-engine pushes, 5 halo by grouped ncclSend/ncclRecv");
   DeviceGuard g;
   std::unique_ptr<ed_sharded> S(new ed_sharded());
   S->ctx = ctx;
@@ -720,9 +788,11 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   // automatic: EDCUDA_SHARD_TRANSPORT (pull | push | cepush), default pull
   int transport = exchange >= 2 ? exchange : 2;
   if (exchange == 0)
-    if (const char* e = getenv("EDCUDA_SHARD_TRANSPORT")) transport = !strcmp(e, "push") ? 3 : !strcmp(e, "cepush") ? 4 : 2;
-  S->push = S->halo && transport >= 3;
+    if (const char* e = getenv("EDCUDA_SHARD_TRANSPORT")) transport = !strcmp(e, "push") ? 3 : !strcmp(e, "cepush") ? 4 : !strcmp(e, "nccl") ? 5 : 2;
+  if (transport == 5 && (ctx->loopback || ctx->world == 1)) transport = 2;      // no NCCL communicator: copy-engine pulls
+  S->push = S->halo && (transport == 3 || transport == 4);
   S->ce_push = S->halo && transport == 4;
+  S->nccl_p2p = S->halo && transport == 5;
   if (const char* e = getenv("EDCUDA_PUSH_CTAS")) S->push_ctas = std::max(1, atoi(e));
   S->rows_of_rank.assign(ctx->world, 0);
   for (int i = 0; i < nl; ++i) {
@@ -750,7 +820,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
         if (S->ce_push) ED_CUDA(cudaMalloc(&Q.send[0], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
       } else {
         Q.halo.alloc((size_t)std::max<int64_t>(Q.L.n_halo, 1) * S->es);
-        for (int b = 0; b < 2; ++b) ED_CUDA(cudaMalloc(&Q.send[b], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
+        for (int b = 0; b < (S->nccl_p2p ? 1 : 2); ++b) ED_CUDA(cudaMalloc(&Q.send[b], (size_t)std::max<int64_t>(Q.L.n_send, 1) * S->es));
       }
       if (!S->push || S->ce_push) {
         std::vector<int64_t> items;
@@ -851,7 +921,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
     }
     ctx_fence(ctx);        // every rank's counters are zeroed before anyone pushes
     ctx_sync(ctx);
-  } else if (S->halo) {
+  } else if (S->halo && !S->nccl_p2p) {
     for (int b = 0; b < 2; ++b) {
       std::vector<void*> mine;
       for (int i = 0; i < nl; ++i) mine.push_back(S->r[i].send[b]);
@@ -903,7 +973,7 @@ int ed_sharded_info(const ed_sharded* sh, int32_t local_index, int64_t* n_local,
   if (n_ranges) *n_ranges = (int32_t)Q.range_lo.size();
   if (n_pulls) *n_pulls = sh->halo ? (int32_t)(sh->push ? Q.L.pushes.size() : Q.L.pulls.size()) : 0;
   if (n_chunks) *n_chunks = sh->halo ? Q.L.n_chunks : 1;
-  if (halo_exchange) *halo_exchange = sh->halo ? (sh->ce_push ? 3 : sh->push ? 2 : 1) : 0;
+  if (halo_exchange) *halo_exchange = sh->halo ? (sh->nccl_p2p ? 4 : sh->ce_push ? 3 : sh->push ? 2 : 1) : 0;
   ED_CATCH
 }
 
@@ -1068,7 +1138,17 @@ int ed_sharded_profile(ed_sharded* sh, ed_dvec* y, ed_dvec* x, double* ms4) {
   };
   ctx_fence(c);
   ed_ctx_timer_record(c, 50);
-  if (sh->push) {
+  if (sh->nccl_p2p) {
+    ed_ctx_timer_record(c, 51);
+    ed_ctx_timer_record(c, 52);
+    sharded_pack(sh, x);                 // pack + the send/recv groups
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ED_CUDA(cudaSetDevice(R.device));
+      ED_CUDA(cudaEventRecord(R.ev, R.push));
+      ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
+    }
+  } else if (sh->push) {
     ed_ctx_timer_record(c, 51);          // no pack pass
     ctx_fence(c);
     ed_ctx_timer_record(c, 52);
@@ -1151,8 +1231,12 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
     ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
     loop_chain(c, i);
   }
-  sharded_pack(sh, u_cur);         // before the all-reduce: the collective doubles as the fence that publishes the pack
+  // pull / push transports: the exchange is started BEFORE the all-reduce, which doubles as its fence; grouped send/recv
+  // shares the communicator with the all-reduce and NCCL runs a communicator's operations in issue order, so there the
+  // all-reduce goes first (it would otherwise wait for the whole halo transfer, and the interior kernels behind it too)
+  if (!sh->nccl_p2p) sharded_pack(sh, u_cur);
   allreduce_at(norms, 0);
+  if (sh->nccl_p2p) sharded_pack(sh, u_cur);
   ed_ctx_timer_record(c, ED_CTX_TIMER_SLOTS - 2);
   for (int j = 0; j < n_steps; ++j) {
     // the peers' send buffers hold their tiles of u_cur: packed before the all-reduce of norms[j] (stream ordered)
@@ -1169,8 +1253,9 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
       loop_chain(c, i);
     }
     std::swap(u_cur, u_prev);
-    if (j + 1 < n_steps) sharded_pack(sh, u_cur);
+    if (j + 1 < n_steps && !sh->nccl_p2p) sharded_pack(sh, u_cur);
     allreduce_at(norms, (size_t)2 * (j + 1));
+    if (j + 1 < n_steps && sh->nccl_p2p) sharded_pack(sh, u_cur);
   }
   ed_ctx_timer_record(c, ED_CTX_TIMER_SLOTS - 1);
   if (ms_per_step) {

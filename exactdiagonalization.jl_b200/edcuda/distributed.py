@@ -188,15 +188,15 @@ class ShardedOperator:
         self.dimension = opr.dimension
         handles = (C.c_void_p * ctx.n_local)(*[o._handle for o in self.oprs])
         h = C.c_void_p()
-        check(lib.ed_sharded_create(ctx._handle, handles, self.code, {"auto": 0, "allgather": 1, "halo": 2, "pull": 2, "push": 3, "cepush": 4}[exchange], n_chunks, C.byref(h)))
+        check(lib.ed_sharded_create(ctx._handle, handles, self.code, {"auto": 0, "allgather": 1, "halo": 2, "pull": 2, "push": 3, "cepush": 4, "nccl": 5}[exchange], n_chunks, C.byref(h)))
         self._handle = h
 
     def info(self, i: int = 0) -> dict:
         nl, nh, nr, npl, nc, he = C.c_int64(), C.c_int64(), C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
         check(lib.ed_sharded_info(self._handle, i, C.byref(nl), C.byref(nh), C.byref(nr), C.byref(npl), C.byref(nc), C.byref(he)))
         return {"n_local": nl.value, "n_halo": nh.value, "n_ranges": nr.value, "n_pulls": npl.value, "n_chunks": nc.value,
-                "exchange": ("allgather", "halo", "halo", "halo")[he.value],
-                "halo_transport": (None, "copy-engine pulls", "owner pushes", "owner copy-engine pushes")[he.value]}
+                "exchange": ("allgather", "halo", "halo", "halo", "halo")[he.value],
+                "halo_transport": (None, "copy-engine pulls", "owner pushes", "owner copy-engine pushes", "nccl send/recv")[he.value]}
 
     def ranges(self, i: int = 0):
         n = self.info(i)["n_ranges"]

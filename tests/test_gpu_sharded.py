@@ -200,6 +200,7 @@ def test_nccl_single_process_context(gpu_ed):
     assert out["info"]["exchange"] == "halo"
     _check_sharded(ed, ctx, 22, 11, "xxz", exchange="push", lanczos_steps=20)
     _check_sharded(ed, ctx, 22, 11, "xxz", exchange="cepush", lanczos_steps=20)
+    assert _check_sharded(ed, ctx, 22, 11, "xxz", exchange="nccl", lanczos_steps=20)["info"]["halo_transport"] == "nccl send/recv"
     _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
     ctx.close()
 
@@ -218,6 +219,7 @@ def _rank_worker(rank, world, port, q):
         out = _check_sharded(ed, ctx, 24, 12, "xxz", lanczos_steps=60)
         _check_sharded(ed, ctx, 22, 11, "xxz", exchange="push", lanczos_steps=20)
         _check_sharded(ed, ctx, 22, 11, "xxz", exchange="cepush", lanczos_steps=20)
+        assert _check_sharded(ed, ctx, 22, 11, "xxz", exchange="nccl", lanczos_steps=20)["info"]["halo_transport"] == "nccl send/recv"
         _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
         ctx.barrier()
         ctx.close()

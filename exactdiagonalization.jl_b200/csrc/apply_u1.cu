@@ -1241,7 +1241,11 @@ std::shared_ptr<U1Global> u1_global_layout(const FastU1Plan* plan, int world, in
           if (j >= 0 && G.owner[j] != r && !seen[j]) { seen[j] = 1; fresh.push_back((uint32_t)j); }
         }
       }
-      std::sort(fresh.begin(), fresh.end(), [&](uint32_t x, uint32_t y) { return G.owner[x] != G.owner[y] ? G.owner[x] < G.owner[y] : x < y; });
+      // peers in ROTATED order (r+1, r+2, ... mod world): at any moment every source is read by one reader -- with all
+      // ranks walking their peers in the same ascending order the seven readers of an 8-rank run would queue up on one
+      // source's NVLink egress at a time
+      auto turn = [&](uint32_t t) { return (G.owner[t] - r - 1 + world) % world; };
+      std::sort(fresh.begin(), fresh.end(), [&](uint32_t x, uint32_t y) { return turn(x) != turn(y) ? turn(x) < turn(y) : x < y; });
       for (uint32_t t : fresh) {
         G.halo_tiles[r].push_back(t);
         G.halo_chunk[r].push_back(ch);
@@ -1327,8 +1331,13 @@ void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunk
     if (!S.piece_pushes.empty() && S.piece_pushes.back().recv == p.recv && S.piece_pushes.back().chunk == p.chunk) S.piece_pushes.back().len += p.len;
     else S.piece_pushes.push_back({p.recv, p.chunk, G.send_off(rank, p.recv, p.chunk), p.dst_off, p.len});
   }
-  std::stable_sort(S.pushes.begin(), S.pushes.end(), [](const U1Push& a, const U1Push& b) { return a.chunk < b.chunk; });
-  std::stable_sort(S.piece_pushes.begin(), S.piece_pushes.end(), [](const U1Push& a, const U1Push& b) { return a.chunk < b.chunk; });
+  // by chunk, receivers in rotated order (rank+1, rank+2, ...): no two owners write the same receiver at the same time
+  auto push_less = [&](const U1Push& a, const U1Push& b) {
+    if (a.chunk != b.chunk) return a.chunk < b.chunk;
+    return (a.recv - rank - 1 + world) % world < (b.recv - rank - 1 + world) % world;
+  };
+  std::stable_sort(S.pushes.begin(), S.pushes.end(), push_less);
+  std::stable_sort(S.piece_pushes.begin(), S.piece_pushes.end(), push_less);
   // packs: for every receiver (ascending) and chunk, its halo tiles owned by this rank, in its halo order
   int64_t send = 0;
   for (int r = 0; r < world; ++r) {

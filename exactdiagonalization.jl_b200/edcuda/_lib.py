@@ -45,6 +45,21 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "(or `make -C exactdiagonalization.jl_b200/csrc`). The engine has no CPU fallback.")
 
+# The multi-GPU context binds NCCL at run time (dlopen of libnccl.so.2).  When PyTorch's bundled copy exists, point the
+# library at it: whichever copy is loaded first under that SONAME is the one PyTorch gets too, and an older system NCCL
+# lacks symbols libtorch_cuda.so needs (ImportError on a later `import torch`).
+if "EDCUDA_NCCL_LIB" not in os.environ:
+    try:
+        import importlib.util as _ilu
+        _spec = _ilu.find_spec("nvidia.nccl")
+        for _loc in (list(_spec.submodule_search_locations) if _spec and _spec.submodule_search_locations else []):
+            _cand = os.path.join(_loc, "lib", "libnccl.so.2")
+            if os.path.exists(_cand):
+                os.environ["EDCUDA_NCCL_LIB"] = _cand
+                break
+    except Exception:
+        pass
+
 lib = C.CDLL(LIB_PATH)
 
 vp, i32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double

@@ -257,6 +257,7 @@ struct ShardRank {
   DevBuf<int> wait_error;                        // set by a wait that timed out
   DevBuf<double> partials;
   std::vector<cudaEvent_t> ev_pull;      // [n_chunks * n_pull_streams]
+  cudaEvent_t ev_side = nullptr;         // pack + fence done on the side stream: the copy engines may pull
   // all-gather exchange
   int64_t row_lo = 0, row_hi = 0;
   DevBuf<unsigned char> x_full;
@@ -271,6 +272,7 @@ struct ed_sharded {
   bool push = false;                         // halo exchange by owner-side pushes (arrival counters) instead of reader-side pulls
   bool ce_push = false;                      // ... pushed by the owner's copy engines from a packed send buffer instead of by SM stores
   bool nccl_p2p = false;                     // halo pieces moved by grouped ncclSend / ncclRecv (one group per launch chunk)
+  bool side = false;                         // pull transport: pack + fence run on the side stream, beside the interior kernels
   int push_ctas = 64;                        // grid of the (persistent) push kernel: a few SMs' worth, the rest keep computing
   int64_t dim = 0;
   size_t es = 8;
@@ -418,6 +420,36 @@ void sharded_pack(ed_sharded* S, ed_dvec* x) {
     return;
   }
   S->parity ^= 1;
+  if (S->side) {
+    // pack and fence on the high-priority side stream: the main stream goes straight on to the interior tiles, which
+    // need neither; the copy engines start when the side stream's fence is through (ev_side)
+    NcclApi& N = nccl();
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ShardRank& Q = S->r[i];
+      ED_CUDA(cudaSetDevice(R.device));
+      ED_CUDA(cudaEventRecord(R.ev, R.stream));           // x final, previous kernels (halo readers) queued before this point
+      ED_CUDA(cudaStreamWaitEvent(R.push, R.ev, 0));
+      if (Q.n_pack_items) {
+        ed_push_stream(R.push);
+        if (S->dtype == ED_F64) ED_LAUNCH(k_pack<double>, Q.n_pack_items, 256, 0, reinterpret_cast<const double*>(x->local[i]), reinterpret_cast<double*>(Q.send[S->parity]), Q.d_packs.p);
+        else ED_LAUNCH(k_pack<double2>, Q.n_pack_items, 256, 0, reinterpret_cast<const double2*>(x->local[i]), reinterpret_cast<double2*>(Q.send[S->parity]), Q.d_packs.p);
+        ed_pop_stream();
+      }
+    }
+    ED_NCCL(N.GroupStart());
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      CtxRank& R = c->local[i];
+      ED_CUDA(cudaSetDevice(R.device));
+      ED_NCCL(N.AllReduce(R.scalars + 7, R.scalars + 7, 1, ncclDouble, ncclSum, R.comm, R.push));
+    }
+    ED_NCCL(N.GroupEnd());
+    for (size_t i = 0; i < c->local.size(); ++i) {
+      ED_CUDA(cudaSetDevice(c->local[i].device));
+      ED_CUDA(cudaEventRecord(S->r[i].ev_side, c->local[i].push));
+    }
+    return;
+  }
   for (size_t i = 0; i < c->local.size(); ++i) {
     ShardRank& Q = S->r[i];
     if (!Q.n_pack_items) continue;
@@ -493,16 +525,21 @@ void sharded_apply(ed_sharded* S, ed_dvec* y, ed_dvec* x, bool packed, bool want
   } else if (S->halo) {
     if (!packed) {
       sharded_pack(S, x);
-      ctx_fence(c);          // every rank's send buffer is complete, and every rank is done with the previous halo
+      if (!S->side) ctx_fence(c);          // every rank's send buffer is complete, and every rank is done with the previous halo
     }
     for (size_t i = 0; i < c->local.size(); ++i) {
       CtxRank& R = c->local[i];
       ShardRank& Q = S->r[i];
       RankScope scope(R);
       const int np = c->n_pull_streams;
-      // release the copy engines at this point of the (fenced) main stream
-      ED_CUDA(cudaEventRecord(R.ev, R.stream));
-      for (int s = 0; s < np; ++s) ED_CUDA(cudaStreamWaitEvent(R.copy[s], R.ev, 0));
+      if (S->side) {
+        // the copy engines wait for the side stream (pack + fence); the main stream does not
+        for (int s = 0; s < np; ++s) ED_CUDA(cudaStreamWaitEvent(R.copy[s], Q.ev_side, 0));
+      } else {
+        // release the copy engines at this point of the (fenced) main stream
+        ED_CUDA(cudaEventRecord(R.ev, R.stream));
+        for (int s = 0; s < np; ++s) ED_CUDA(cudaStreamWaitEvent(R.copy[s], R.ev, 0));
+      }
       size_t ip = 0;
       int k = 0;
       for (int ch = 0; ch < Q.L.n_chunks; ++ch) {
@@ -793,6 +830,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
   S->push = S->halo && (transport == 3 || transport == 4);
   S->ce_push = S->halo && transport == 4;
   S->nccl_p2p = S->halo && transport == 5;
+  S->side = S->halo && transport == 2 && !ctx->loopback && ctx->world > 1 && !(getenv("EDCUDA_SHARD_SIDE") && atoi(getenv("EDCUDA_SHARD_SIDE")) == 0);
   if (const char* e = getenv("EDCUDA_PUSH_CTAS")) S->push_ctas = std::max(1, atoi(e));
   S->rows_of_rank.assign(ctx->world, 0);
   for (int i = 0; i < nl; ++i) {
@@ -833,6 +871,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
       Q.partials.alloc((size_t)2 * std::max<size_t>(Q.L.tile_H.size(), 1));
       Q.ev_pull.resize((size_t)Q.L.n_chunks * ED_CTX_PULL_STREAMS);
       for (auto& e : Q.ev_pull) ED_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ED_CUDA(cudaEventCreateWithFlags(&Q.ev_side, cudaEventDisableTiming));
       ED_CUDA(cudaStreamSynchronize(R.stream));
     } else {
       for (int r = 0; r < ctx->world; ++r) {
@@ -954,6 +993,7 @@ int ed_sharded_destroy(ed_sharded* sh) {
     cudaSetDevice(c->local[i].device);
     ShardRank& Q = sh->r[i];
     for (auto& e : Q.ev_pull) cudaEventDestroy(e);
+    if (Q.ev_side) cudaEventDestroy(Q.ev_side);
     for (int b = 0; b < 2; ++b) if (Q.send[b]) cudaFree(Q.send[b]);
     if (Q.halo_mem) cudaFree(Q.halo_mem);
     Q.d_push.release(); Q.wait_error.release();
@@ -1164,7 +1204,10 @@ int ed_sharded_profile(ed_sharded* sh, ed_dvec* y, ed_dvec* x, double* ms4) {
       ED_CUDA(cudaStreamWaitEvent(R.stream, R.ev, 0));
     }
   } else {
+    const bool side = sh->side;          // the phases are timed one after another on the main stream
+    sh->side = false;
     sharded_pack(sh, x);
+    sh->side = side;
     ed_ctx_timer_record(c, 51);
     ctx_fence(c);
     ed_ctx_timer_record(c, 52);
@@ -1234,9 +1277,10 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
   // pull / push transports: the exchange is started BEFORE the all-reduce, which doubles as its fence; grouped send/recv
   // shares the communicator with the all-reduce and NCCL runs a communicator's operations in issue order, so there the
   // all-reduce goes first (it would otherwise wait for the whole halo transfer, and the interior kernels behind it too)
-  if (!sh->nccl_p2p) sharded_pack(sh, u_cur);
+  const bool pack_after = sh->nccl_p2p || sh->side;      // these issue their own collective on the side stream
+  if (!pack_after) sharded_pack(sh, u_cur);
   allreduce_at(norms, 0);
-  if (sh->nccl_p2p) sharded_pack(sh, u_cur);
+  if (pack_after) sharded_pack(sh, u_cur);
   ed_ctx_timer_record(c, ED_CTX_TIMER_SLOTS - 2);
   for (int j = 0; j < n_steps; ++j) {
     // the peers' send buffers hold their tiles of u_cur: packed before the all-reduce of norms[j] (stream ordered)
@@ -1253,9 +1297,9 @@ int ed_lanczos_sharded(ed_sharded* sh, int32_t n_steps, uint64_t seed, ed_dvec* 
       loop_chain(c, i);
     }
     std::swap(u_cur, u_prev);
-    if (j + 1 < n_steps && !sh->nccl_p2p) sharded_pack(sh, u_cur);
+    if (j + 1 < n_steps && !pack_after) sharded_pack(sh, u_cur);
     allreduce_at(norms, (size_t)2 * (j + 1));
-    if (j + 1 < n_steps && sh->nccl_p2p) sharded_pack(sh, u_cur);
+    if (j + 1 < n_steps && pack_after) sharded_pack(sh, u_cur);
   }
   ed_ctx_timer_record(c, ED_CTX_TIMER_SLOTS - 1);
   if (ms_per_step) {

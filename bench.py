@@ -282,7 +282,7 @@ def bench_tri6x6(ed, np, ctx, steps, peak):
     n_local = sh.info(0)["n_local"]
     alg = 40.0 * n_local                       # 8 B word + 16 B x + 16 B y per owned row
     out = {"workload": "tri6x6_k0A1_sz0", "dim": d, "parent_dim": 9075135300, "n_terms": len(h.terms), "group_order": len(symops),
-           "dtype": "c128", "rows_per_gpu": n_local, "exchange": "none" if ctx.world == 1 else "NCCL all-gather of x per matvec (in-library)",
+           "dtype": "c128", "rows_per_gpu": n_local, "exchange": "none" if ctx.world == 1 else "NCCL all-gather of x per matvec (in-library), window by window on a side stream; the cached SpMV's column-block pass b starts when window b is there",
            "setup_seconds": t_setup,
            "matrix_free": {"ms_per_matvec": ms_free, "matvec_per_s": 1e3 / ms_free, "gnnz_per_s": nnz / (ms_free * 1e-3) / 1e9,
                            "roofline": {"bound": "hbm", "achieved": alg / (ms_free * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -258,6 +258,7 @@ struct ShardRank {
   DevBuf<double> partials;
   std::vector<cudaEvent_t> ev_pull;      // [n_chunks * n_pull_streams]
   cudaEvent_t ev_side = nullptr;         // pack + fence done on the side stream: the copy engines may pull
+  std::vector<cudaEvent_t> ev_win;       // windowed all-gather: x of column window w has arrived
   // all-gather exchange
   int64_t row_lo = 0, row_hi = 0;
   DevBuf<unsigned char> x_full;
@@ -275,6 +276,7 @@ struct ed_sharded {
   bool side = false;                         // pull transport: pack + fence run on the side stream, beside the interior kernels
   int push_ctas = 64;                        // grid of the (persistent) push kernel: a few SMs' worth, the rest keep computing
   int64_t dim = 0;
+  int64_t win_cols = 0;                      // all-gather exchange: x travels in windows of this many rows (0 = in one piece)
   size_t es = 8;
   std::vector<ShardRank> r;                  // per local rank
   std::vector<int64_t> rows_of_rank;         // [world]
@@ -581,13 +583,66 @@ void sharded_apply(ed_sharded* S, ed_dvec* y, ed_dvec* x, bool packed, bool want
     std::vector<int64_t> bytes(c->world), offs(c->world);
     for (int r = 0; r < c->world; ++r) { bytes[r] = S->rows_of_rank[r] * (int64_t)S->es; offs[r] = S->row_offset[r] * (int64_t)S->es; }
     for (size_t i = 0; i < c->local.size(); ++i) { send.push_back(x->local[i]); recv.push_back(S->r[i].x_full.p); }
-    if (c->world > 1) ctx_allgatherv(c, send, recv, bytes, offs);
+    // NCCL contexts gather x window by window on the side stream (the windows of the column-blocked cached SpMV, the same
+    // on every rank): pass b of a cached matrix starts when window b has arrived, the later windows travel under it.
+    // Every other kernel waits for the last window.
+    const int n_win = (c->world > 1 && !c->loopback && S->win_cols > 0) ? (int)((S->dim + S->win_cols - 1) / S->win_cols) : 0;
+    if (n_win > 1) {
+      NcclApi& N = nccl();
+      for (size_t i = 0; i < c->local.size(); ++i) {
+        CtxRank& R = c->local[i];
+        ShardRank& Q = S->r[i];
+        ED_CUDA(cudaSetDevice(R.device));
+        while ((int)Q.ev_win.size() < n_win) {
+          cudaEvent_t e;
+          ED_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+          Q.ev_win.push_back(e);
+        }
+        ED_CUDA(cudaEventRecord(R.ev, R.stream));          // x final; the previous readers of x_full are queued before this
+        ED_CUDA(cudaStreamWaitEvent(R.push, R.ev, 0));
+      }
+      for (int w = 0; w < n_win; ++w) {
+        const int64_t w_lo = (int64_t)w * S->win_cols, w_hi = std::min<int64_t>(S->dim, w_lo + S->win_cols);
+        ED_NCCL(N.GroupStart());
+        for (size_t i = 0; i < c->local.size(); ++i) {
+          CtxRank& R = c->local[i];
+          ED_CUDA(cudaSetDevice(R.device));
+          for (int root = 0; root < c->world; ++root) {
+            const int64_t lo = std::max<int64_t>(w_lo, S->row_offset[root]);
+            const int64_t hi = std::min<int64_t>(w_hi, S->row_offset[root] + S->rows_of_rank[root]);
+            if (hi <= lo) continue;
+            char* dst = static_cast<char*>(recv[i]) + (size_t)lo * S->es;
+            const char* src = R.rank == root ? static_cast<const char*>(send[i]) + (size_t)(lo - S->row_offset[root]) * S->es : dst;
+            ED_NCCL(N.Broadcast(src, dst, (size_t)(hi - lo) * S->es, ncclChar, root, R.comm, R.push));
+          }
+        }
+        ED_NCCL(N.GroupEnd());
+        for (size_t i = 0; i < c->local.size(); ++i) {
+          ED_CUDA(cudaSetDevice(c->local[i].device));
+          ED_CUDA(cudaEventRecord(S->r[i].ev_win[w], c->local[i].push));
+        }
+      }
+    } else if (c->world > 1) {
+      ctx_allgatherv(c, send, recv, bytes, offs);
+    }
     for (size_t i = 0; i < c->local.size(); ++i) {
       RankScope scope(c->local[i]);
       ShardRank& Q = S->r[i];
       const void* xin = c->world > 1 ? (const void*)Q.x_full.p : (const void*)x->local[i];
+      bool gated = false;
+      if (n_win > 1) {
+        const CsrCache* cc = Q.op->csr[ED_SIDE_LEFT].get();
+        gated = cc && Q.op->kernel_choice != 1 && cc->n_blocks == n_win && cc->block_cols == S->win_cols;
+        if (gated) ed_csr_set_column_gate(Q.ev_win.data(), n_win);
+        else ED_CUDA(cudaStreamWaitEvent(c->local[i].stream, Q.ev_win[n_win - 1], 0));
+      }
       if (Q.row_hi > Q.row_lo) {
         const int rc = ed_apply_async(Q.op, y->local[i], xin, S->dtype, ED_SIDE_LEFT, 0, want_dot ? Q.dot.p : nullptr);
+        if (gated) {
+          ed_csr_set_column_gate(nullptr, 0);
+          // the later kernels of this stream must not overtake the windows either (a pass may have been skipped)
+          ED_CUDA(cudaStreamWaitEvent(c->local[i].stream, Q.ev_win[n_win - 1], 0));
+        }
         ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
       } else if (want_dot) {
         ED_CUDA(cudaMemsetAsync(Q.dot.p, 0, 2 * sizeof(double), c->local[i].stream));
@@ -886,6 +941,7 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
       const int rc = ed_oprep_set_rows(Q.op, Q.row_lo, Q.row_hi);
       ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
       if (ctx->world > 1) Q.x_full.alloc((size_t)S->dim * S->es);
+      if (!(getenv("EDCUDA_SHARD_WINDOWS") && atoi(getenv("EDCUDA_SHARD_WINDOWS")) == 0)) S->win_cols = ed_csr_window_cols(Q.op);
     }
   }
   S->row_offset.assign(ctx->world + 1, 0);
@@ -994,6 +1050,7 @@ int ed_sharded_destroy(ed_sharded* sh) {
     ShardRank& Q = sh->r[i];
     for (auto& e : Q.ev_pull) cudaEventDestroy(e);
     if (Q.ev_side) cudaEventDestroy(Q.ev_side);
+    for (auto& e : Q.ev_win) cudaEventDestroy(e);
     for (int b = 0; b < 2; ++b) if (Q.send[b]) cudaFree(Q.send[b]);
     if (Q.halo_mem) cudaFree(Q.halo_mem);
     Q.d_push.release(); Q.wait_error.release();

@@ -295,6 +295,10 @@ struct CsrCache {
   std::vector<int64_t> blk_base;      // [n_blocks + 1] first entry of block b in col / val
 };
 
+struct ed_oprep;
+int64_t ed_csr_window_cols(const ed_oprep* o);                     // sparse.cu: columns per pass of the column-blocked SpMV
+void ed_csr_set_column_gate(const cudaEvent_t* ev, int n);         // sparse.cu: pass b waits for ev[b]; (nullptr, 0) clears
+
 struct ed_oprep {
   ed_basis* basis = nullptr;    // plain representation: its basis; reduced: the parent basis
   ed_rbasis* rbasis = nullptr;  // non-null for ReducedOperatorRepresentation

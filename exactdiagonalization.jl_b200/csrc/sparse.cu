@@ -541,10 +541,9 @@ k_spmv_csr_blk(int64_t n_rows, int64_t row_lo, const uint32_t* __restrict__ rowp
   }
 }
 
-// regroup the row-major cached matrix into column blocks (see above); leaves it untouched when one block suffices
-static void csr_block_columns(ed_oprep* o, CsrCache* c) {
-  const int64_t n = c->row_hi - c->row_lo;
-  if (n <= 0 || c->nnz <= 0) return;
+// columns per pass of a column-blocked cached matrix = the x window kept in L2.  Depends on the operator and the device
+// model only, so every rank of a sharded operator gets the same windows (ctx.cu gathers x window by window).
+int64_t ed_csr_window_cols(const ed_oprep* o) {
   int dev = 0, l2 = 0;
   ED_CUDA(cudaGetDevice(&dev));
   ED_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, dev));
@@ -554,9 +553,24 @@ static void csr_block_columns(ed_oprep* o, CsrCache* c) {
   // 8.65 / 8.37 / 8.60 -- every extra pass re-reads the row pointers and y, so the window is as large as the L2 allows
   int64_t W = std::max<int64_t>(4096, (int64_t)(0.67 * (double)l2) / elem);
   if (const char* e = getenv("EDCUDA_CSR_BLOCK_COLS")) { const long long v = atoll(e); if (v > 0) W = v; }
-  if (W >= o->dim) return;
   int64_t B = (o->dim + W - 1) / W;
-  if (B > 32) { B = 32; W = (o->dim + B - 1) / B; B = (o->dim + W - 1) / W; }
+  if (B > 32) { B = 32; W = (o->dim + B - 1) / B; }
+  return W;
+}
+
+// per-thread gate of the column-blocked SpMV: pass b first waits for ev[b] (x of window b has arrived)
+static thread_local const cudaEvent_t* t_gate_ev = nullptr;
+static thread_local int t_gate_n = 0;
+void ed_csr_set_column_gate(const cudaEvent_t* ev, int n) { t_gate_ev = ev; t_gate_n = n; }
+
+// regroup the row-major cached matrix into column blocks (see above); leaves it untouched when one block suffices
+static void csr_block_columns(ed_oprep* o, CsrCache* c) {
+  const int64_t n = c->row_hi - c->row_lo;
+  if (n <= 0 || c->nnz <= 0) return;
+  const int64_t W0 = ed_csr_window_cols(o);
+  if (W0 >= o->dim) return;
+  int64_t W = W0;
+  const int64_t B = (o->dim + W - 1) / W;
   DevBuf<uint32_t> cnt((size_t)B * (n + 1));
   ED_CUDA(cudaMemsetAsync(cnt.p, 0, (size_t)B * (n + 1) * sizeof(uint32_t), ed_stream()));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)ed_sm_count() * 16));
@@ -700,6 +714,7 @@ void ed_apply_csr(ed_oprep* o, void* out, const void* x, int dtype, int side, in
     // lanes per row: 4 measured best (8: 9.26 ms, 4: 8.37, 2: 11.9, 1: 15.8 at 4 blocks; rows hold ~14 entries per block)
     const int lanes = getenv("EDCUDA_CSR_LANES") ? atoi(getenv("EDCUDA_CSR_LANES")) : 4;
     for (int b = 0; b < c->n_blocks; ++b) {
+      if (t_gate_ev && b < t_gate_n) ED_CUDA(cudaStreamWaitEvent(ed_stream(), t_gate_ev[b], 0));
       const uint32_t* rp = c->blk_rowptr.p + (size_t)b * (n + 1);
       const int32_t* cb = c->col.p + c->blk_base[b];
       const int mode = (accumulate || b > 0) ? 1 : 0;

@@ -131,19 +131,17 @@ def test_loopback_world1_and_lanczos_matches_single_gpu(gpu_ed, golden):
         sh.close(); ctx.close()
 
 
-def test_loopback_reduced_representation_allgather(gpu_ed):
-    """config 4's machinery at a size the oracle follows: reduced representation, rows sharded, x all-gathered."""
-    ed = gpu_ed
-    from edcuda.distributed import Context, ShardedOperator
+def _check_reduced(ed, make_ctx, n, k):
+    """reduced representation (translation irrep k) of the Heisenberg chain: rows sharded, x all-gathered; matrix-free and cached"""
+    from edcuda.distributed import ShardedOperator
     from helpers import to_oracle_symops
-    n = 12
     hs, h = ed.models.heisenberg_chain(n)
     hs_o, h_o = oracle_spin_chain(n)
-    symops = ed.lattices.chain_translation_irrep(n, 5)
+    symops = ed.lattices.chain_translation_irrep(n, k)
     rhsr_o = O.symmetry_reduce(O.represent(O.HilbertSpaceSector(hs_o, 0)), to_oracle_symops(symops))
     ropr_o = O.ReducedOperatorRepresentation(rhsr_o, h_o)
     for cached in (False, True):
-        ctx = Context.single_process([0, 0, 0])
+        ctx = make_ctx()
 
         def make():
             ropr = ed.represent(ed.symmetry_reduce(ed.represent(ed.HilbertSpaceSector(hs, 0)), symops), h)
@@ -160,10 +158,18 @@ def test_loopback_reduced_representation_allgather(gpu_ed):
         x = rng.standard_normal(d) + 1j * rng.standard_normal(d)
         xv, yv = sh.vector(), sh.vector()
         xv.upload(x)
-        sh.apply(yv, xv)
         exp = O.apply_serial(np.zeros(d, dtype=complex), ropr_o, x, "left")
-        assert rel_err(yv.download(), exp) < TOL
+        for _ in range(3):                     # repeated: the gather of matvec n+1 must not overtake the kernels of matvec n
+            dot = sh.apply(yv, xv, dot=True)
+            assert rel_err(yv.download(), exp) < TOL
+            assert abs(dot - np.vdot(x, exp)) < 1e-10 * max(1.0, abs(np.vdot(x, exp)))
         xv.close(); yv.close(); sh.close(); ctx.close()
+
+
+def test_loopback_reduced_representation_allgather(gpu_ed):
+    """config 4's machinery at a size the oracle follows: reduced representation, rows sharded, x all-gathered."""
+    from edcuda.distributed import Context
+    _check_reduced(gpu_ed, lambda: Context.single_process([0, 0, 0]), 12, 5)
 
 
 def test_sharded_argument_errors(gpu_ed):
@@ -203,6 +209,22 @@ def test_nccl_single_process_context(gpu_ed):
     assert _check_sharded(ed, ctx, 22, 11, "xxz", exchange="nccl", lanczos_steps=20)["info"]["halo_transport"] == "nccl send/recv"
     _check_sharded(ed, ctx, 20, 7, "j1j2", exchange="allgather")
     ctx.close()
+
+
+def test_nccl_windowed_allgather_cached_csr(gpu_ed, monkeypatch):
+    """x gathered window by window on the side stream, the column-blocked cached SpMV pass b gated on window b
+    (ctx.cu: sharded_apply, sparse.cu: ed_csr_set_column_gate); small windows forced so that a 810-row sector has 9 of them."""
+    ed = gpu_ed
+    from edcuda.distributed import Context
+    n_gpu = min(ed.device_count(), 4)
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    monkeypatch.setenv("EDCUDA_CSR_BLOCK_COLS", "100")
+    _check_reduced(ed, lambda: Context.single_process(list(range(n_gpu))), 16, 3)
+    monkeypatch.setenv("EDCUDA_CSR_BLOCK_COLS", "37")              # windows that cut through every rank's piece
+    _check_reduced(ed, lambda: Context.single_process(list(range(n_gpu))), 14, 0)
+    monkeypatch.setenv("EDCUDA_SHARD_WINDOWS", "0")                # blocked SpMV behind the one-piece gather
+    _check_reduced(ed, lambda: Context.single_process(list(range(n_gpu))), 14, 0)
 
 
 def _rank_worker(rank, world, port, q):

@@ -164,6 +164,16 @@ __device__ __forceinline__ uint64_t sym_apply(const SymDesc& S, int g, uint64_t 
 
 // index of `key` in the ascending representative list, bucketed by the top bits.
 __device__ __forceinline__ int64_t rank_reduced(const RLookupDesc& R, uint64_t key) {
+  if (R.hash) {
+    const uint64_t slot_mask = ~0ull >> R.hash_shift;
+    uint64_t s = (key * 0x9E3779B97F4A7C15ull) >> R.hash_shift;
+    for (;;) {
+      const unsigned long long e = __ldg(R.hash + s);
+      if (e == ~0ull) return -1;                                        // load factor <= 1/2: an empty slot ends every probe
+      if ((e >> R.idx_bits) == key) return (int64_t)(e & ((1ull << R.idx_bits) - 1));
+      s = (s + 1) & slot_mask;
+    }
+  }
   uint64_t b = key >> R.bucket_shift;
   if (b >= (uint64_t)R.n_buckets) return -1;
   int64_t lo = __ldg(R.bucket_start + b), hi = __ldg(R.bucket_start + b + 1);

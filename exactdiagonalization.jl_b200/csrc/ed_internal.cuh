@@ -259,7 +259,13 @@ struct ed_rbasis {
   int bucket_shift = 0;
   DevBuf<uint32_t> bucket_start;  // [n_buckets+1]
   int64_t n_buckets = 0;
+  // hash index word -> reduced index (open addressing, one 8-byte slot = word << idx_bits | index): one memory access per
+  // look-up where the bucketed search needs ~log2(bucket) dependent ones (orbit minima crowd into few top-bit buckets).
+  // Built when word and index fit one slot together; otherwise the bucketed search stays the only index.
+  DevBuf<unsigned long long> hash;
+  int hash_shift = 0, idx_bits = 0;
   SymDesc symdesc() const;
+  struct RLookupDesc rdesc() const;
 };
 
 struct RLookupDesc {
@@ -270,6 +276,9 @@ struct RLookupDesc {
   int bucket_shift;
   int64_t n_buckets;
   int64_t dim;
+  const unsigned long long* hash;   // nullptr: bucketed binary search only
+  int hash_shift;                   // slot = (word * golden) >> hash_shift
+  int idx_bits;
 };
 
 // ------------------------------------------------------------------ operator representation

@@ -29,14 +29,7 @@ static WalkCtx make_walk_ctx(ed_oprep* o, int side) {
     W.reduced = 1;
     W.words = o->rbasis->words.p;
     W.S = o->rbasis->symdesc();
-    RLookupDesc R;
-    R.words = o->rbasis->words.p;
-    R.orbit_size = o->rbasis->orbit_size.p;
-    R.last_stab = o->rbasis->last_stab.p;
-    R.bucket_start = o->rbasis->bucket_start.p;
-    R.bucket_shift = o->rbasis->bucket_shift;
-    R.n_buckets = o->rbasis->n_buckets;
-    R.dim = o->rbasis->dim;
+    const RLookupDesc R = o->rbasis->rdesc();
     W.R = R;
   } else {
     W.words = o->basis->words.p;

@@ -97,14 +97,7 @@ void ed_apply_reduced(ed_oprep* o, void* out, const void* x, int side, int accum
     if (alpha_dot) ED_CUDA(cudaMemsetAsync(alpha_dot, 0, 2 * sizeof(double), ed_stream()));
     return;
   }
-  RLookupDesc R;
-  R.words = rb->words.p;
-  R.orbit_size = rb->orbit_size.p;
-  R.last_stab = rb->last_stab.p;
-  R.bucket_start = rb->bucket_start.p;
-  R.bucket_shift = rb->bucket_shift;
-  R.n_buckets = rb->n_buckets;
-  R.dim = rb->dim;
+  const RLookupDesc R = rb->rdesc();
   const int block = 128;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + block - 1) / block, (int64_t)ed_sm_count() * 16));
   DevBuf<double>& partial_buf = ed_scratch<double, 3>();

@@ -585,9 +585,7 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
     else if (nch <= 6) ED_LAUNCH(k6b_canonicalize<6>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
     else if (nch <= 8) ED_LAUNCH(k6b_canonicalize<8>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
     else ED_LAUNCH(k6b_canonicalize<11>, grid_b, 256, 0, S.n_ops, lut6, inv, n_hits, sc.words.p, sc.garg.p);
-    RLookupDesc R;
-    R.words = rb->words.p; R.orbit_size = rb->orbit_size.p; R.last_stab = rb->last_stab.p;
-    R.bucket_start = rb->bucket_start.p; R.bucket_shift = rb->bucket_shift; R.n_buckets = rb->n_buckets; R.dim = rb->dim;
+    const RLookupDesc R = rb->rdesc();
     const int grid_l = (int)std::max<int64_t>(1, std::min<int64_t>((n_hits + 255) / 256, (int64_t)sm * 32));
     ED_LAUNCH(k6b_lookup, grid_l, 256, 0, R, n_hits, sc.words.p, sc.hitj.p, sc.horb.p);
   }
@@ -610,9 +608,7 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
   const TermsDev& TD = side == ED_SIDE_LEFT ? o->terms_left : o->terms_right;
   K6Terms T{TD.n_terms, TD.mask.p, TD.match.p, TD.target.p, TD.amp.p, TD.is_complex ? 1 : 0};
   const int64_t n_rows = o->row_hi - o->row_lo;
-  RLookupDesc R;
-  R.words = rb->words.p; R.orbit_size = rb->orbit_size.p; R.last_stab = rb->last_stab.p;
-  R.bucket_start = rb->bucket_start.p; R.bucket_shift = rb->bucket_shift; R.n_buckets = rb->n_buckets; R.dim = rb->dim;
+  const RLookupDesc R = rb->rdesc();
   const SymDesc S = rb->symdesc();
   const LookupDesc L = parent->desc();
   K6Scratch& sc = scratch();
@@ -663,9 +659,7 @@ bool ed_reduced_fill_raw_staged(ed_oprep* o, int side, int64_t line0, int64_t n,
   if (parent->kind == ED_BASIS_LIST) parent->materialize();
   const TermsDev& TD = side == ED_SIDE_LEFT ? o->terms_left : o->terms_right;
   K6Terms T{TD.n_terms, TD.mask.p, TD.match.p, TD.target.p, TD.amp.p, TD.is_complex ? 1 : 0};
-  RLookupDesc R;
-  R.words = rb->words.p; R.orbit_size = rb->orbit_size.p; R.last_stab = rb->last_stab.p;
-  R.bucket_start = rb->bucket_start.p; R.bucket_shift = rb->bucket_shift; R.n_buckets = rb->n_buckets; R.dim = rb->dim;
+  const RLookupDesc R = rb->rdesc();
   const SymDesc S = rb->symdesc();
   const LookupDesc L = parent->desc();
   K6Scratch& sc = scratch();

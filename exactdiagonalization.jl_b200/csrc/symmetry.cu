@@ -195,17 +195,21 @@ SymDesc ed_rbasis::symdesc() const {
   return S;
 }
 
-static RLookupDesc rdesc(const ed_rbasis* r) {
+RLookupDesc ed_rbasis::rdesc() const {
   RLookupDesc R;
-  R.words = r->words.p;
-  R.orbit_size = r->orbit_size.p;
-  R.last_stab = r->last_stab.p;
-  R.bucket_start = r->bucket_start.p;
-  R.bucket_shift = r->bucket_shift;
-  R.n_buckets = r->n_buckets;
-  R.dim = r->dim;
+  R.words = words.p;
+  R.orbit_size = orbit_size.p;
+  R.last_stab = last_stab.p;
+  R.bucket_start = bucket_start.p;
+  R.bucket_shift = bucket_shift;
+  R.n_buckets = n_buckets;
+  R.dim = dim;
+  R.hash = hash.n ? hash.p : nullptr;
+  R.hash_shift = hash_shift;
+  R.idx_bits = idx_bits;
   return R;
 }
+static RLookupDesc rdesc(const ed_rbasis* r) { return r->rdesc(); }
 
 // ------------------------------------------------------------------ K5: representative filter
 // One thread per parent word of the chunk [lo, lo+n).  A word survives iff no group element maps it
@@ -322,8 +326,41 @@ static void build_rbasis(ed_rbasis* r) {
   ed_rbasis_finish_index(r);
 }
 
-// bucket index over the top bits of the (ascending) representatives: narrows the binary search of the reduced lookup
+__global__ void __launch_bounds__(256)
+k_rhash_insert(const uint64_t* __restrict__ words, int64_t dim, unsigned long long* __restrict__ hash, int hash_shift, int idx_bits) {
+  const uint64_t slot_mask = ~0ull >> hash_shift;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < dim; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = words[i];
+    const unsigned long long e = (key << idx_bits) | (unsigned long long)i;
+    uint64_t s = (key * 0x9E3779B97F4A7C15ull) >> hash_shift;
+    while (atomicCAS(hash + s, ~0ull, e) != ~0ull) s = (s + 1) & slot_mask;
+  }
+}
+
+// indices over the (ascending) representatives for the reduced lookup: buckets over the top bits (narrow the binary search)
+// and, when a word and its index fit 64 bits together, the hash table rank_reduced prefers (EDCUDA_RBASIS_HASH=0: none,
+// saves 16 bytes per representative)
 void ed_rbasis_finish_index(ed_rbasis* r) {
+  r->hash.release();
+  r->hash_shift = r->idx_bits = 0;
+  {
+    const int bits_w = r->parent->space.bits;
+    const char* e = getenv("EDCUDA_RBASIS_HASH");
+    if (r->dim > 0 && bits_w >= 1 && bits_w <= 63 && !(e && atoi(e) == 0)) {
+      const int idx_bits = 64 - bits_w;
+      const bool fits = idx_bits >= 63 || (uint64_t)r->dim <= (1ull << idx_bits) - 1;     // the index field is never all ones
+      if (fits) {
+        int lg = 4;
+        while ((1ll << lg) < 2 * r->dim) ++lg;
+        r->hash.alloc((size_t)1 << lg);
+        ED_CUDA(cudaMemsetAsync(r->hash.p, 0xFF, sizeof(unsigned long long) << lg, ed_stream()));
+        r->hash_shift = 64 - lg;
+        r->idx_bits = idx_bits;
+        const int grid = (int)std::min<int64_t>((r->dim + 255) / 256, (int64_t)ed_sm_count() * 16);
+        ED_LAUNCH(k_rhash_insert, grid, 256, 0, r->words.p, r->dim, r->hash.p, r->hash_shift, r->idx_bits);
+      }
+    }
+  }
   const int64_t used = r->dim;
   ED_REQUIRE(used < (1ll << 32), ED_ERR_UNSUPPORTED, "reduced dimension exceeds 2^32");
   const int bits = r->parent->space.bits;

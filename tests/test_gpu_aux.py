@@ -156,3 +156,28 @@ def test_lanczos_stops_at_invariant_subspace(gpu_ed):
     sector = np.linalg.eigvalsh(ed.represent(rhsr, h).matrix())
     assert abs(res.ritz[0] - sector[0]) < 1e-9                               # lowest level of the k=0 sector
     assert all(np.min(np.abs(full - r)) < 1e-7 for r in res.ritz)           # no ghosts
+
+
+def test_reduced_lookup_hash_and_buckets_agree(gpu_ed, monkeypatch):
+    """the reduced index is looked up through the hash table (default) or the bucketed binary search (EDCUDA_RBASIS_HASH=0):
+    same matvec bit for bit, same basis mapping, same reduce / unreduce of a vector; the staged and the row-per-thread kernels"""
+    ed = gpu_ed
+    n = 16
+    hs, h = ed.models.heisenberg_chain(n)
+    symops = ed.lattices.chain_translation_irrep(n, 3)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("EDCUDA_RBASIS_HASH", mode)
+        hsr = ed.represent(ed.HilbertSpaceSector(hs, 0))
+        rhsr = ed.symmetry_reduce(hsr, symops)
+        x = np.random.default_rng(1).standard_normal(rhsr.dimension) * (1 + 0.5j)
+        res = []
+        for min_rows in ("1", "1000000"):                                # staged kernel / row-per-thread kernel
+            monkeypatch.setenv("EDCUDA_K6_MIN_ROWS", min_rows)
+            res.append(ed.represent(rhsr, h) * x)
+        big = np.random.default_rng(2).standard_normal(hsr.dimension) + 0j
+        out[mode] = (res, rhsr.basis_mapping_index.copy(), ed.symmetry_reduce(rhsr, big), ed.symmetry_unreduce(rhsr, x))
+    for a, b in zip(out["1"][0] + [out["1"][1], out["1"][3]], out["0"][0] + [out["0"][1], out["0"][3]]):
+        assert np.array_equal(a, b)
+    assert rel_err(out["1"][2], out["0"][2]) < 1e-13                     # the reduce kernel sums orbit members with atomics
+    assert rel_err(out["1"][0][0], out["1"][0][1]) < 1e-12

@@ -941,7 +941,11 @@ int ed_sharded_create(ed_ctx* ctx, ed_oprep* const* opreps, int32_t dtype, int32
       const int rc = ed_oprep_set_rows(Q.op, Q.row_lo, Q.row_hi);
       ED_REQUIRE(rc == ED_OK, rc, ed_last_error());
       if (ctx->world > 1) Q.x_full.alloc((size_t)S->dim * S->es);
-      if (!(getenv("EDCUDA_SHARD_WINDOWS") && atoi(getenv("EDCUDA_SHARD_WINDOWS")) == 0)) S->win_cols = ed_csr_window_cols(Q.op);
+      // windowed gather (see sharded_apply): measured on config 4's cached SpMV, 2 / 4 / 8 ranks: 4.65 -> 4.45 ms, 2.65 -> 2.90,
+      // 1.74 -> 2.11 -- with more ranks a window holds few roots' pieces and the per-group NCCL latency outweighs the overlap,
+      // so it is the default for two ranks only (EDCUDA_SHARD_WINDOWS=1 / 0 forces it on / off)
+      const char* we = getenv("EDCUDA_SHARD_WINDOWS");
+      if (we ? atoi(we) != 0 : ctx->world == 2) S->win_cols = ed_csr_window_cols(Q.op);
     }
   }
   S->row_offset.assign(ctx->world + 1, 0);

@@ -219,6 +219,7 @@ def test_nccl_windowed_allgather_cached_csr(gpu_ed, monkeypatch):
     n_gpu = min(ed.device_count(), 4)
     if n_gpu < 2:
         pytest.skip("needs at least 2 GPUs")
+    monkeypatch.setenv("EDCUDA_SHARD_WINDOWS", "1")                # (the default only for two ranks)
     monkeypatch.setenv("EDCUDA_CSR_BLOCK_COLS", "100")
     _check_reduced(ed, lambda: Context.single_process(list(range(n_gpu))), 16, 3)
     monkeypatch.setenv("EDCUDA_CSR_BLOCK_COLS", "37")              # windows that cut through every rank's piece

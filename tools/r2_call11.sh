@@ -17,6 +17,5 @@ PY
   tail -2 gpurun_out/r2c11_$name.err
 }
 BARGS="" run n8_full 8 X=1
-BARGS="--no-extras --no-e2e" run n8_side0 8 EDCUDA_SHARD_SIDE=0
 BARGS="--no-extras --no-e2e" run n8_norefine 8 EDCUDA_SHARD_REFINE=0
 BARGS="" run n4_full 4 X=1

@@ -320,6 +320,8 @@ struct ed_oprep {
   bool terms_ready = false;
   std::shared_ptr<FastU1Plan> u1plan, u1plan_c;  // f64 / c128 vectors
   std::shared_ptr<CsrCache> csr[2];               // per side, built by ed_oprep_cache_matrix
+  std::vector<int64_t> k6_hits[2];                // staged reduced matvec: emitted column words per row batch, per side
+  int64_t k6_hits_lo = -1, k6_hits_hi = -1, k6_hits_batch = -1;   // ... valid for this row range and batch size
   // sparse() result kept between ed_sparse_count and ed_sparse_fetch
   DevBuf<int64_t> sp_colptr, sp_rowval;
   DevBuf<double> sp_nzval;

@@ -385,6 +385,159 @@ k6b_canonicalize_nk(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict_
   }
 }
 
+// B (necklace, two-row keys, queued).  What limits k6b_canonicalize_nk (ncu source page): its running-minimum filter on ONE
+// row lets most cosets through -- the four point-group elements that keep a line direction produce the same rows, rows with at
+// most two particles equal their mirror necklace, and an empty row is minimal under every shift: 10 (coset, row, shift)
+// candidates per word on the 6x6 lattice -- and one candidate lane sends its whole warp down the comparison path (42 % of the
+// instructions at 18 of 32 lanes).  Here
+//   * the key is the top TWO rows: a 2^(2 n1)-entry table gives, for (row y, row y-1), the smallest pair under a common shift
+//     and the shifts reaching it, so ties are broken inside the table (about 1.5 candidates per word);
+//   * pass A (uniform, branch-free) finds m* = the smallest key over ALL cosets of a word and the cosets attaining it;
+//   * pass B (warp-cooperative): the (word, coset) pairs of a warp are compacted into a shared-memory queue and handed out one
+//     per lane; a pair rebuilds its image, walks the (row, shift) candidates that reach m* and folds word || element into the
+//     word's slot with a 64-bit shared-memory atomicMin.
+// The minimum over the group has top rows m*, so every element attaining it is among the candidates: (best, besti) as in the
+// full sweep.  key = word << 16 | (0xFFFF - inverse index): smallest word first, then the LARGEST inverse index (the Dict
+// overwrite).  CTAs are persistent (tables built once per CTA, all coset tables resident).
+template <int NCH, int N1, int N2>
+__global__ void __launch_bounds__(256)
+k6b_canonicalize_nkq(int n_cos, int n1_rt, int n2_rt, const uint64_t* __restrict__ lut6c, const int32_t* __restrict__ tinv,
+                     int64_t n_words, uint64_t* __restrict__ words, uint16_t* __restrict__ garg) {
+  constexpr int W = 2;          // words per thread and block
+  constexpr bool FIXED = N1 > 0;
+  const int n1 = FIXED ? N1 : n1_rt, n2 = FIXED ? N2 : n2_rt, n_bits = n1 * n2;
+  const int nt = n1 * n2;
+  extern __shared__ __align__(16) unsigned char k6_smem[];
+  uint64_t* s_lut = reinterpret_cast<uint64_t*>(k6_smem);                   // [n_cos][NCH * 64]
+  uint64_t* s_mlo = s_lut + (size_t)n_cos * NCH * 64;                       // [8] columns x < a of every row
+  uint64_t* s_w = s_mlo + 8;                                                // [8 warps][32] words of the half in flight
+  unsigned long long* s_best = reinterpret_cast<unsigned long long*>(s_w + 256);   // [8][32]
+  int32_t* s_inv = reinterpret_cast<int32_t*>(s_best + 256);                // [n_cos][n1 * n2]
+  uint32_t* s_ms = reinterpret_cast<uint32_t*>(s_inv + (size_t)n_cos * nt); // [8][32] m* of those words
+  uint16_t* s_q = reinterpret_cast<uint16_t*>(s_ms + 256);                  // [8][32 * n_cos] queue entries lane << 8 | coset
+  uint16_t* s_key = s_q + (size_t)8 * 32 * n_cos;                           // [2^(2 n1)] smallest (top, next) pair under a common shift
+  uint8_t* s_sh = reinterpret_cast<uint8_t*>(s_key + ((size_t)1 << (2 * n1)));   // [2^(2 n1)] the shifts reaching it
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t full = n_bits >= 64 ? ~0ull : ((1ull << n_bits) - 1ull);
+  const uint32_t rmask = (1u << n1) - 1u;
+  const uint32_t pmask = (1u << (2 * n1)) - 1u;
+  for (int i = tid; i < n_cos * NCH * 64; i += 256) s_lut[i] = __ldg(lut6c + i);
+  for (int i = tid; i < n_cos * nt; i += 256) s_inv[i] = __ldg(tinv + i);
+  for (int v = tid; v < (1 << (2 * n1)); v += 256) {
+    uint32_t top = ((uint32_t)v >> n1) & rmask, nxt = (uint32_t)v & rmask;
+    uint32_t best = (uint32_t)v, arg = 1u;
+    for (int a = 1; a < n1; ++a) {
+      top = ((top << 1) | (top >> (n1 - 1))) & rmask;          // rotate both rows left by one: Tx
+      nxt = ((nxt << 1) | (nxt >> (n1 - 1))) & rmask;
+      const uint32_t r = (top << n1) | nxt;
+      if (r < best) { best = r; arg = 1u << a; }
+      else if (r == best) arg |= 1u << a;
+    }
+    s_key[v] = (uint16_t)best;
+    s_sh[v] = (uint8_t)arg;
+  }
+  if (tid < 8) {
+    uint64_t m = 0;
+    for (int y = 0; y < n2; ++y) m |= (uint64_t)((1u << tid) - 1u) << (n1 * y);
+    s_mlo[tid] = tid <= n1 ? (m & full) : 0ull;
+  }
+  __syncthreads();
+  uint64_t* my_w = s_w + warp * 32;
+  unsigned long long* my_best = s_best + warp * 32;
+  uint32_t* my_ms = s_ms + warp * 32;
+  uint16_t* my_q = s_q + (size_t)warp * 32 * n_cos;
+  const int wrap_shift = n_bits - n1;                                       // the top row, wrapped below row 0 for y = 0
+  for (int64_t base = (int64_t)blockIdx.x * (256 * W); base < n_words; base += (int64_t)gridDim.x * (256 * W)) {
+    uint64_t w[W];
+    uint32_t off[W][NCH];
+    uint32_t mstar[W], cosets[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      const int64_t i = base + tid + k * 256;
+      w[k] = i < n_words ? words[i] : 0ull;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) off[k][c] = (uint32_t)((w[k] >> (6 * c)) & 63ull) + c * 64;
+      mstar[k] = 0xFFFFu;
+      cosets[k] = 0u;
+    }
+    // ---- pass A
+#pragma unroll 2
+    for (int j = 0; j < n_cos; ++j) {
+      const uint64_t* L = s_lut + (size_t)j * NCH * 64;
+#pragma unroll
+      for (int k = 0; k < W; ++k) {
+        uint64_t v = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) v |= L[off[k][c]];
+        // (row 0, row n2-1) first, then (row y, row y-1) as contiguous 2 n1-bit windows
+        uint32_t mm = s_key[(((uint32_t)v & rmask) << n1) | (uint32_t)(v >> wrap_shift)];
+#pragma unroll(FIXED ? N2 - 1 : 1)
+        for (int y = 1; y < n2; ++y) mm = min(mm, (uint32_t)s_key[(uint32_t)(v >> (n1 * (y - 1))) & pmask]);
+        cosets[k] = mm < mstar[k] ? (1u << j) : (mm == mstar[k] ? (cosets[k] | (1u << j)) : cosets[k]);
+        mstar[k] = min(mstar[k], mm);
+      }
+    }
+    // ---- pass B, one half (the k-th word of every lane) at a time
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+      my_w[lane] = w[k];
+      my_best[lane] = ~0ull;
+      my_ms[lane] = mstar[k];
+      uint32_t cs = (base + tid + k * 256) < n_words ? cosets[k] : 0u;      // padding lanes queue nothing
+      const int cnt = __popc(cs);
+      int pre = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pre, o);
+        if (lane >= o) pre += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, pre, 31);
+      int pos = pre - cnt;
+      while (cs) {
+        const int j = __ffs(cs) - 1;
+        cs &= cs - 1u;
+        my_q[pos++] = (uint16_t)((lane << 8) | j);
+      }
+      __syncwarp();
+#pragma unroll 1
+      for (int it = lane; it < total; it += 32) {
+        const uint32_t e = my_q[it];
+        const int wl = (int)(e >> 8), j = (int)(e & 255u);
+        const uint64_t ww = my_w[wl];
+        const uint32_t ms = my_ms[wl];
+        const uint64_t* L = s_lut + (size_t)j * NCH * 64;
+        const int32_t* inv_tab = s_inv + (size_t)j * nt;
+        uint64_t im = 0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) im |= L[(uint32_t)((ww >> (6 * c)) & 63ull) + c * 64];
+        unsigned long long lb = ~0ull;
+#pragma unroll 1
+        for (int y = 0; y < n2; ++y) {
+          const uint32_t idx = y ? ((uint32_t)(im >> (n1 * (y - 1))) & pmask) : ((((uint32_t)im & rmask) << n1) | (uint32_t)(im >> wrap_shift));
+          if ((uint32_t)s_key[idx] != ms) continue;
+          const int b = n2 - 1 - y;                  // Ty^b brings row y to the top (and row y-1 below it)
+          const uint64_t ub = b ? (((im << (n1 * b)) | (im >> (n_bits - n1 * b))) & full) : im;
+          uint32_t shifts = s_sh[idx];
+          while (shifts) {                          // usually one shift
+            const int a = __ffs(shifts) - 1;
+            shifts &= shifts - 1u;
+            const uint64_t mlo = s_mlo[a];
+            const uint64_t u = a ? (((ub << a) & full & ~mlo) | ((ub >> (n1 - a)) & mlo)) : ub;     // Tx^a
+            const unsigned long long key = (u << 16) | (unsigned long long)(0xFFFF - inv_tab[b * n1 + a]);
+            lb = key < lb ? key : lb;
+          }
+        }
+        atomicMin(my_best + wl, lb);
+      }
+      __syncwarp();
+      const unsigned long long key = my_best[lane];
+      const int64_t i = base + tid + k * 256;
+      if (i < n_words) { words[i] = key >> 16; garg[i] = (uint16_t)(0xFFFFu - (uint32_t)(key & 0xFFFFull)); }
+      __syncwarp();
+    }
+  }
+}
+
 // B': representative index and orbit size of every canonical word, word-parallel (independent searches: the memory
 // latency of the bucketed binary search is hidden by parallelism instead of sitting inside the per-row combine loop)
 __global__ void __launch_bounds__(256)
@@ -517,7 +670,10 @@ static K6Scratch& scratch() {
 
 // Phases A + B for rows [row0, row0 + nb): sc.offs = exclusive offsets of the off-diagonal hits per row, sc.words = the
 // orbit minimum of every hit, sc.garg = the element the reference's Dict keeps for it.  Returns the number of hits.
-static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64_t nb, K6Scratch& sc, cudaEvent_t ev_mid) {
+// *known_hits >= 0: the number of column words this batch emits is known from an earlier matvec of the same representation --
+// no count read-back, no host synchronisation; < 0: read it back and store it there
+static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64_t nb, K6Scratch& sc, cudaEvent_t ev_mid,
+                              int64_t* known_hits = nullptr) {
   ed_rbasis* rb = o->rbasis;
   ed_basis* parent = rb->parent;
   const SymDesc S = rb->symdesc();
@@ -533,8 +689,13 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
   cub::DeviceScan::ExclusiveSum(sc.tmp.p, bytes, sc.counts.p, sc.offs.p, nb + 1, ed_stream());
   g_launch_count.fetch_add(1, std::memory_order_relaxed);
   int64_t n_hits = 0;
-  ED_CUDA(cudaMemcpyAsync(&n_hits, sc.offs.p + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));
-  ED_CUDA(cudaStreamSynchronize(ed_stream()));
+  if (known_hits && *known_hits >= 0) {
+    n_hits = *known_hits;
+  } else {
+    ED_CUDA(cudaMemcpyAsync(&n_hits, sc.offs.p + nb, sizeof(int64_t), cudaMemcpyDeviceToHost, ed_stream()));
+    ED_CUDA(cudaStreamSynchronize(ed_stream()));
+    if (known_hits) *known_hits = n_hits;
+  }
   if (sc.words.n < (size_t)std::max<int64_t>(n_hits, 1)) {
     sc.words.alloc((size_t)std::max<int64_t>(n_hits, 1));
     sc.garg.alloc((size_t)std::max<int64_t>(n_hits, 1));
@@ -553,6 +714,27 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
     if (sd.tr_on && nch <= 8 && sd.tr_n1 <= 8 && sd.tr_n1 >= 2 && parent->space.bits == sd.tr_n1 * sd.tr_n2 && !no_necklace) {
       const int nt_ = sd.tr_n1 * sd.tr_n2;
       const int grid_n = (int)((n_hits + 511) / 512);
+      // two-row keys + queued comparisons when n1 <= 6 (2^(2 n1)-entry table), the tables of all cosets fit shared memory, the
+      // coset set fits a 32-bit mask and word || element fits 64 bits (EDCUDA_K6_NK1=1: the one-pass kernel)
+      static const bool one_pass = getenv("EDCUDA_K6_NK1") != nullptr;
+      const int nch_t = (sd.tr_n1 == 6 && sd.tr_n2 == 6 && nch == 6) ? 6 : (nch <= 4 ? 4 : (nch <= 6 ? 6 : 8));
+      const size_t smem_q = (size_t)sd.tr_ncos * nch_t * 64 * 8 + 8 * 8 + 256 * 8 + 256 * 8 + (size_t)sd.tr_ncos * nt_ * 4 + 256 * 4 +
+                            (size_t)8 * 32 * sd.tr_ncos * 2 + ((size_t)3 << (2 * sd.tr_n1));
+      if (!one_pass && sd.tr_n1 <= 6 && sd.tr_n2 >= 2 && sd.tr_ncos <= 32 && nt_ <= 48 && smem_q <= 72 * 1024) {
+        const int grid_q = (int)std::min<int64_t>((n_hits + 511) / 512, (int64_t)sm * 3);
+#define ED_K6NKQ(NCH_, N1_, N2_)                                                                                             \
+        do {                                                                                                                 \
+          ED_CUDA(cudaFuncSetAttribute(k6b_canonicalize_nkq<NCH_, N1_, N2_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q)); \
+          ED_LAUNCH((k6b_canonicalize_nkq<NCH_, N1_, N2_>), grid_q, 256, smem_q, sd.tr_ncos, sd.tr_n1, sd.tr_n2, sd.tr_lut6.p, \
+                    sd.tr_inv.p, n_hits, sc.words.p, sc.garg.p);                                                             \
+        } while (0)
+        if (sd.tr_n1 == 6 && sd.tr_n2 == 6 && nch == 6) ED_K6NKQ(6, 6, 6);
+        else if (sd.tr_n1 == 4 && sd.tr_n2 == 4 && nch <= 4) ED_K6NKQ(4, 4, 4);
+        else if (nch <= 4) ED_K6NKQ(4, 0, 0);
+        else if (nch <= 6) ED_K6NKQ(6, 0, 0);
+        else ED_K6NKQ(8, 0, 0);
+#undef ED_K6NKQ
+      } else {
 #define ED_K6NK(NCH_, N1_, N2_)                                                                                              \
       do {                                                                                                                   \
         const size_t smem_n = (size_t)2 * 4 * NCH_ * 64 * 8 + (size_t)(2 * 4 * nt_ + ((2 * 4 * nt_) & 1)) * 4 + 8 * 8 + ((size_t)2 << sd.tr_n1) + \
@@ -566,6 +748,7 @@ static int64_t k6_stage_batch(ed_oprep* o, const K6Terms& T, int64_t row0, int64
       else if (nch <= 6) ED_K6NK(6, 0, 0);
       else ED_K6NK(8, 0, 0);
 #undef ED_K6NK
+      }
     }
     else if (sd.tr_on && nch <= 8) {
       const size_t smem = (size_t)2 * 4 * nch * 64 * 8 + (size_t)2 * 4 * sd.tr_n1 * sd.tr_n2 * 4;
@@ -620,6 +803,14 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
   const int grid_c_max = sm * 16;
   if (alpha_dot && sc.partials.n < (size_t)2 * grid_c_max * n_batches) sc.partials.alloc((size_t)2 * grid_c_max * n_batches);
   int slots_used = 0;
+  // hit counts per batch of this (side, row range, batching): filled by the first matvec, after which the loop never waits
+  // for the device
+  std::vector<int64_t>& hits_cache = o->k6_hits[side == ED_SIDE_RIGHT ? 1 : 0];
+  if (o->k6_hits_lo != o->row_lo || o->k6_hits_hi != o->row_hi || o->k6_hits_batch != batch_rows) {
+    o->k6_hits[0].clear(); o->k6_hits[1].clear();
+    o->k6_hits_lo = o->row_lo; o->k6_hits_hi = o->row_hi; o->k6_hits_batch = batch_rows;
+  }
+  if (hits_cache.size() != (size_t)n_batches) hits_cache.assign((size_t)n_batches, -1);
   // EDCUDA_K6_TIMING=1: per-phase device times of this call on stderr (profiling aid; adds event records only)
   static const bool timing = getenv("EDCUDA_K6_TIMING") != nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -629,7 +820,7 @@ void ed_apply_reduced_staged(ed_oprep* o, void* out, const void* x, int side, in
     if (timing) ED_CUDA(cudaEventRecord(ev[0], ed_stream()));
     const int64_t nb = std::min(batch_rows, n_rows - b0);
     const int64_t row0 = o->row_lo + b0;
-    const int64_t n_hits = k6_stage_batch(o, T, row0, nb, sc, timing ? ev[1] : nullptr);
+    const int64_t n_hits = k6_stage_batch(o, T, row0, nb, sc, timing ? ev[1] : nullptr, &hits_cache[(size_t)(b0 / batch_rows)]);
     if (timing) ED_CUDA(cudaEventRecord(ev[2], ed_stream()));
     const int grid_c = (int)std::max<int64_t>(1, std::min<int64_t>((nb + 127) / 128, (int64_t)grid_c_max));
     ED_LAUNCH(k6c_combine, grid_c, 128, (size_t)3 * T.n_terms * sizeof(uint64_t), T, L, S, R, row0, nb, b0, sc.offs.p, sc.hitj.p, sc.horb.p, sc.garg.p,

@@ -288,7 +288,7 @@ def bench_tri6x6(ed, np, ctx, steps, peak):
                            "roofline": {"bound": "hbm", "achieved": alg / (ms_free * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                         "frac": alg / (ms_free * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg},
                            "gpu_launches": int(launches_free), "kernel": "K6 staged (emit / canonicalize / combine)",
-                           "note": "instruction-bound (orbit search per off-diagonal hit), not HBM-bound (SURVEY H1)"},
+                           "note": "bound by shared-memory table look-ups of the orbit search per off-diagonal hit, not by HBM (SURVEY H1)"},
            "cached_csr": {"nnz": nnz, "assemble_seconds": t_cache, "ms_per_matvec": ms_csr, "matvec_per_s": 1e3 / ms_csr,
                           "gnnz_per_s": nnz / (ms_csr * 1e-3) / 1e9,
                           "roofline": {"bound": "hbm", "achieved": alg / (ms_csr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

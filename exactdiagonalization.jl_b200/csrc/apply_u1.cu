@@ -85,9 +85,36 @@ struct U1Params {
   const int64_t* dir;
   const void* x_local;
   const void* x_halo;
+  int x_bulk;                   // x_local is 16-byte aligned: the tile is staged with one TMA bulk copy (cp.async.bulk) per CTA
 };
 
 #define U1_DIR_HALO (1ll << 62)
+#define U1_XS_EXTRA 4           // slots of the staged x tile beyond tile_cap: alignment shift, zero padding target, rounding
+
+// the staged-tile bulk copy needs a 16-byte aligned vector (EDCUDA_U1_NOBULK=1: per-thread loads, same results)
+static inline int u1_bulk_ok(const void* x) {
+  static const bool off = getenv("EDCUDA_U1_NOBULK") != nullptr;
+  return (!off && (reinterpret_cast<uintptr_t>(x) & 15u) == 0) ? 1 : 0;
+}
+
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (sm_90+: UBLKCP / SYNCS in SASS)
+__device__ __forceinline__ uint32_t u1_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void u1_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  const uint32_t b = u1_smem_addr(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(1) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(u1_smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void u1_bulk_wait(unsigned long long* bar) {
+  const uint32_t b = u1_smem_addr(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(b), "r"(0) : "memory");
+  } while (!ok);
+}
 
 // neighbour tile H2 under the exchange mode: false = this pass does not read it
 template <typename VecT>
@@ -406,8 +433,8 @@ template <typename VecT, int THREADS, int R>
 __global__ void __launch_bounds__(THREADS, (R <= 7 && sizeof(VecT) == 8) ? 3 : 2)
 k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_partials) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  VecT* xs = reinterpret_cast<VecT*>(smem_raw);                       // tile_cap + 1 (last = 0: ELL padding target)
-  double* hh_amp = reinterpret_cast<double*>(xs + P.tile_cap + 1);
+  VecT* xs_store = reinterpret_cast<VecT*>(smem_raw);                 // tile_cap + U1_XS_EXTRA slots, 16-byte aligned
+  double* hh_amp = reinterpret_cast<double*>(xs_store + P.tile_cap + U1_XS_EXTRA);
   double* mx_amp = hh_amp + U1_MAX_HH;
   double* mq_coef = mx_amp + U1_MAX_MX;
   double* s_dval = mq_coef + U1_MAX_MQ;                                // 256
@@ -420,6 +447,7 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   double* ms_amp = reinterpret_cast<double*>(ms_len + U1_MAX_MS);
   const VecT** ms_ptr = reinterpret_cast<const VecT**>(ms_amp + U1_MAX_MS);
   __shared__ int s_counts[4];
+  __shared__ __align__(8) unsigned long long s_bar;
 
   const int tid = threadIdx.x;
   const uint32_t H = P.tile_H[P.tile_order ? P.tile_order[blockIdx.x] : P.tile_first + blockIdx.x];
@@ -429,6 +457,21 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
   // position of the tile in x_local (and, minus row_lo, in y): its global rank, or its slot in this rank's shard
   const int64_t base = P.dir ? P.dir[H] : (int64_t)P.tile_base[H];
   const int k = P.k;
+  // x tile in shared memory: xs[0 .. size) = x[base .. base + size), xs[size] = 0 (the ELL padding target).  With a 16-byte
+  // aligned vector the tile comes in through ONE bulk copy issued by thread 0 while the other warps build the bond lists:
+  // from the 16-byte boundary at or below the tile (Float64: xs is shifted by one slot for odd `base`), whole 16-byte units
+  // only -- a trailing half unit and the zero slot are written by thread 0 itself, so the copy never touches them and never
+  // reads past the tile.
+  const uint32_t mis = (sizeof(VecT) == 8 && P.x_bulk) ? (uint32_t)(base & 1) : 0u;
+  VecT* xs = xs_store + mis;
+  const uint32_t bulk_elems = P.x_bulk ? (sizeof(VecT) == 8 ? ((mis + size) & ~1u) : size) : 0u;   // in VecT units from xs_store
+  const bool bulk = bulk_elems > 0 && P.stream_mode != 2;
+  if (bulk && tid == 0) {
+    const VecT* src = reinterpret_cast<const VecT*>(P.x_local) + (base - mis);
+    u1_bulk_load(xs_store, src, bulk_elems * (uint32_t)sizeof(VecT), &s_bar);
+    if (bulk_elems < mis + size) xs_store[bulk_elems] = ldg_val(src + bulk_elems);   // odd tail
+    xs[size] = vzero((VecT*)nullptr);
+  }
 
   // ---- prologue: per-tile bond lists (deterministic ballot compaction), x tile --------------------------
   if (tid < 32) {
@@ -529,12 +572,13 @@ k2_apply_u1(const U1Params P, VecT* __restrict__ y, double* __restrict__ dot_par
       return;
     }
   }
-  {
+  if (!bulk) {
     const VecT* xo = reinterpret_cast<const VecT*>(P.x_local) + base;
     for (uint32_t i = tid; i < size; i += THREADS) xs[i] = ldg_val(xo + i);
+    if (tid == 0) xs[size] = vzero((VecT*)nullptr);
   }
-  if (tid == 0) xs[size] = vzero((VecT*)nullptr);
   __syncthreads();
+  if (bulk) u1_bulk_wait(&s_bar);
 
   U1Tile<VecT> T;
   T.xs = xs;
@@ -961,7 +1005,7 @@ static std::shared_ptr<FastU1Plan> build_plan(const ed_operator& op, int n_bits,
   P.hh_p = plan->hh_p.p; P.hh_q = plan->hh_q.p; P.hh_amp = plan->hh_amp.p;
   P.mx_q = plan->mx_q.p; P.mx_amp = plan->mx_amp.p; P.mx_tab = plan->mx_tab.p;
   P.ms_q = plan->ms_q.p; P.ms_amp = plan->ms_amp.p;
-  plan->smem_bytes = (size_t)(tile_cap + 1) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
+  plan->smem_bytes = (size_t)(tile_cap + U1_XS_EXTRA) * vec_bytes + (U1_MAX_HH + U1_MAX_MX + U1_MAX_MQ + 256) * 8 +
                      (U1_MAX_HH + U1_MAX_MX) * 8 + (U1_MAX_MX + U1_MAX_MQ) * 4 + U1_MAX_MS * (4 + 4 + 8 + 8);
   plan->smem_bytes = (plan->smem_bytes + 15) & ~(size_t)15;
   plan->supported = true;
@@ -1468,6 +1512,7 @@ void ed_apply_u1(ed_oprep* o, void* out, const void* x, int dtype, int side, int
   P.stream_mode = 0;
   P.dir = nullptr;
   P.x_local = x;
+  P.x_bulk = u1_bulk_ok(x);
   P.x_halo = nullptr;
   P.partial_first = 0;
   u1_fill_params(o, P);
@@ -1507,6 +1552,7 @@ void ed_apply_u1_sharded(ed_oprep* o, int dtype, const U1ShardLaunch& L) {
   if (P.stream_mode == 2) P.n_ll = 0;      // remote pass: neighbour streams only, added to what the local pass wrote
   P.dir = L.dir;
   P.x_local = L.x_local;
+  P.x_bulk = u1_bulk_ok(L.x_local);
   P.x_halo = L.x_halo;
   P.tile_H = L.tile_H;
   P.tile_first = L.first;

@@ -1379,10 +1379,29 @@ void ed_u1_shard_layout(const FastU1Plan* plan, int world, int rank, int n_chunk
   ED_REQUIRE(world >= 1 && rank >= 0 && rank < world && n_chunks >= 1, ED_ERR_ARGUMENT, "bad rank / world / chunks");
   // the global layout is the same for every rank: cached per (plan, world, chunks, policy) so that a process driving
   // several GPUs computes it once
-  static thread_local struct { const FastU1Plan* plan = nullptr; int world = 0, chunks = 0, policy = 0; size_t nt = 0; std::shared_ptr<U1Global> G; } cache;
-  if (!(cache.G && cache.plan == plan && cache.world == world && cache.chunks == n_chunks && cache.policy == policy && cache.nt == plan->h_tile_H.size())) {
+  // keyed by CONTENT (everything u1_global_layout reads: tiles, bond lists, world, chunks, policy, the refinement switch),
+  // never by the plan's address -- a freed plan's address can come back with another operator behind it
+  uint64_t sig = 1469598103934665603ull;
+  auto mix = [&](const void* data, size_t bytes) {
+    const unsigned char* b = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < bytes; ++i) { sig ^= b[i]; sig *= 1099511628211ull; }
+  };
+  {
+    const char* re = getenv("EDCUDA_SHARD_REFINE");
+    const int64_t head[10] = {world, n_chunks, policy, plan->hb, plan->k, plan->wraps ? 1 : 0, plan->n_hh, plan->n_mx, plan->n_ms,
+                              (re && atoi(re) == 0) ? 0 : 1};
+    mix(head, sizeof(head));
+    mix(plan->h_tile_H.data(), plan->h_tile_H.size() * sizeof(uint32_t));
+    mix(plan->h_size.data(), plan->h_size.size() * sizeof(uint64_t));
+    mix(plan->h_hh_p.data(), plan->h_hh_p.size());
+    mix(plan->h_hh_q.data(), plan->h_hh_q.size());
+    mix(plan->h_mx_q.data(), plan->h_mx_q.size());
+    mix(plan->h_ms_q.data(), plan->h_ms_q.size());
+  }
+  static thread_local struct { uint64_t sig = 0; size_t nt = 0; std::shared_ptr<U1Global> G; } cache;
+  if (!(cache.G && cache.sig == sig && cache.nt == plan->h_tile_H.size())) {
     cache.G = u1_global_layout(plan, world, n_chunks, policy);
-    cache.plan = plan; cache.world = world; cache.chunks = n_chunks; cache.policy = policy; cache.nt = plan->h_tile_H.size();
+    cache.sig = sig; cache.nt = plan->h_tile_H.size();
   }
   const U1Global& G = *cache.G;
   const size_t nt = plan->h_tile_H.size();

@@ -271,3 +271,28 @@ def test_world2_gloo_halo_exchange_and_lanczos():
 
     a_ref, b_ref = O.lanczos(mv, v0, steps)
     assert np.allclose(alphas, a_ref, atol=1e-9) and np.allclose(betas, b_ref, atol=1e-9)
+
+
+def test_refinement_trades_row_balance_for_halo(ed, monkeypatch):
+    """the local refinement of the tile cut (csrc/apply_u1.cu: u1_global_layout) lowers the largest halo where the transfer
+    dominates, keeps every shard within a bounded row imbalance, covers the basis exactly once and is the same on every rank"""
+    n, n_dn, world, chunks = 26, 13, 8, 8
+    terms = _terms(n, "xxz")
+    monkeypatch.setenv("EDCUDA_SHARD_REFINE", "0")
+    plain = [describe(ed, terms, n, n_dn, world, r, chunks, 0) for r in range(world)]
+    monkeypatch.delenv("EDCUDA_SHARD_REFINE")
+    fine = [describe(ed, terms, n, n_dn, world, r, chunks, 0) for r in range(world)]
+    dim = fine[0]["dim"]
+    assert sum(p["n_local"] for p in fine) == dim == sum(p["n_local"] for p in plain)
+    cover = np.zeros(dim, dtype=np.int32)
+    for p in fine:
+        for lo, hi in p["ranges"]:
+            cover[lo:hi] += 1
+    assert cover.min() == 1 and cover.max() == 1
+    halo_plain, halo_fine = max(p["n_halo"] for p in plain), max(p["n_halo"] for p in fine)
+    rows_fine = max(p["n_local"] for p in fine)
+    assert halo_fine <= halo_plain
+    assert max(rows_fine, 1.5 * halo_fine) <= max(max(p["n_local"] for p in plain), 1.5 * halo_plain)   # the objective it minimises
+    assert rows_fine <= 1.25 * dim / world
+    again = describe(ed, terms, n, n_dn, world, 3, chunks, 0)                # a second evaluation (another rank's view): identical
+    assert np.array_equal(again["ranges"], fine[3]["ranges"]) and again["n_halo"] == fine[3]["n_halo"]

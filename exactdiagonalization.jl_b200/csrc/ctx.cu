@@ -48,15 +48,19 @@ struct NcclApi {
 };
 
 NcclApi& nccl() {
-  static NcclApi api;
-  if (api.handle) return api;
+  static NcclApi ready;
+  if (ready.handle) return ready;
+  NcclApi api;                         // published only when every symbol resolved
   const char* names[] = {getenv("EDCUDA_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
     if (!n) continue;
     api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
     if (api.handle) break;
   }
-  ED_REQUIRE(api.handle, ED_ERR_UNSUPPORTED, std::string("cannot load NCCL (libnccl.so.2): ") + (dlerror() ? dlerror() : ""));
+  if (!api.handle) {
+    const char* why = dlerror();
+    throw EdError(ED_ERR_UNSUPPORTED, std::string("cannot load NCCL (libnccl.so.2): ") + (why ? why : ""));
+  }
 #define ED_NCCL_SYM(name)                                                                  \
   api.name = reinterpret_cast<decltype(api.name)>(dlsym(api.handle, "nccl" #name));        \
   ED_REQUIRE(api.name, ED_ERR_UNSUPPORTED, "libnccl lacks nccl" #name)
@@ -64,7 +68,8 @@ NcclApi& nccl() {
   ED_NCCL_SYM(CommDestroy); ED_NCCL_SYM(AllReduce); ED_NCCL_SYM(AllGather); ED_NCCL_SYM(Broadcast);
   ED_NCCL_SYM(GroupStart); ED_NCCL_SYM(GroupEnd); ED_NCCL_SYM(GetErrorString); ED_NCCL_SYM(Send); ED_NCCL_SYM(Recv);
 #undef ED_NCCL_SYM
-  return api;
+  ready = api;
+  return ready;
 }
 
 #define ED_NCCL(call)                                                                                     \

@@ -407,7 +407,10 @@ end
 mutable struct ShardedOperator{S}
     ptr::Ptr{Cvoid}; ctx::Context; oprs::Vector{Any}; dim::Int
 end
-# make(dev) builds the representation on device `dev` (the library's current device is set before the call)
+# make(dev) builds the representation on device `dev` (the library's current device is set before the call).
+# exchange: 0 = automatic (tiled kernel: halo exchange by copy-engine pulls; everything else: NCCL all-gather of x),
+#           1 = all-gather, 2 = pulls, 3 = owner SM pushes, 4 = owner copy-engine pushes, 5 = grouped ncclSend/ncclRecv;
+# chunks:   launch chunks per matvec for the halo exchange (0 = the library's default, 8)
 function ShardedOperator(ctx::Context, make::Function; exchange::Integer=0, chunks::Integer=0)
     oprs = Any[]
     for dev in ctx.devices

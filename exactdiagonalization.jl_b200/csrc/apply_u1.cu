@@ -22,9 +22,11 @@
 //     that lives in L2.
 //   * row-owner writes: deterministic, no atomics; the Lanczos <x, Hx> partial is fused in the epilogue.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <random>
+#include <thread>
 
 #include "ed_device.cuh"
 
@@ -1226,78 +1228,120 @@ std::shared_ptr<U1Global> u1_global_layout(const FastU1Plan* plan, int world, in
   std::vector<uint32_t> order, best_order;
   std::vector<int> owner;
   uint64_t best = ~0ull;
-  for (const KeySpec& K : cands) {
-    u1_order_by_key(plan, K, order);
+  std::vector<std::pair<uint64_t, size_t>> ranked;           // (largest halo of the plain cut, candidate)
+  for (size_t ci = 0; ci < cands.size(); ++ci) {
+    u1_order_by_key(plan, cands[ci], order);
     u1_cut(plan, order, world, owner);
     const uint64_t h = world > 1 ? u1_max_halo(plan, TG, owner, world) : 0;
-    if (h < best) { best = h; best_order = order; G.owner = owner; G.key_name = K.name; }
+    ranked.push_back({h, ci});
+    if (h < best) { best = h; best_order = order; G.owner = owner; G.key_name = cands[ci].name; }
     if (world == 1) break;
   }
   // ---- local refinement of the cut (policy 0 only): move single tiles between ranks while that lowers
   //      max over the two ranks of max(rows, rho * halo rows)   [or keeps it and lowers the halo sum],
   // rho = 1.5 = measured cost of one halo row (8 B at the ~400 GB/s the copy engines reach over NVLink in an 8-rank
   // exchange) over one kernel row (7.86 ms / 6.0e8).  Where the transfer dominates (4 and 8 ranks at L=32) this trades a
-  // few per cent of row balance for a third less halo (L=32, 8 ranks: largest halo 0.99e8 -> 0.67e8 rows); where the
-  // kernel dominates (2 ranks) the row term keeps the balance.  Deterministic (fixed-seed shuffle): every rank computes
-  // the same partition.  EDCUDA_SHARD_REFINE=0 switches it off.
+  // few per cent of row balance for less halo; where the kernel dominates (2 ranks) the row term keeps the balance.
+  // The descent stops in a local optimum that depends on where it starts, so it is run from the EDCUDA_SHARD_STARTS (16)
+  // best plain cuts, on host threads, and the partition with the smallest max over ranks of max(rows, rho * halo) wins
+  // (L=32, 8 ranks: largest halo 0.99e8 plain -> 0.62e8 refined from the best plain cut -> 0.55e8 from the best of 16).
+  // Deterministic (fixed-seed shuffles, ties to the better plain cut): every rank computes the same partition.
+  // EDCUDA_SHARD_REFINE=0 switches it off.
   if (world > 1 && policy == 0 && !(getenv("EDCUDA_SHARD_REFINE") && atoi(getenv("EDCUDA_SHARD_REFINE")) == 0)) {
     const double rho = 1.5;
-    std::vector<int>& owner_r = G.owner;
-    std::vector<std::vector<int32_t>> cnt(world, std::vector<int32_t>(nt, 0));     // cnt[r][n]: tiles of r that read n
-    std::vector<double> rows(world, 0.0), halo(world, 0.0);
-    for (size_t t = 0; t < nt; ++t) {
-      rows[owner_r[t]] += (double)plan->h_size[t];
-      const int32_t* row = TG.nbr.data() + t * TG.deg;
-      for (int d = 0; d < TG.deg; ++d) if (row[d] >= 0) ++cnt[owner_r[t]][row[d]];
-    }
-    for (int r = 0; r < world; ++r)
-      for (size_t n = 0; n < nt; ++n) if (cnt[r][n] > 0 && owner_r[n] != r) halo[r] += (double)plan->h_size[n];
-    auto obj = [&](double rw, double hl) { return std::max(rw, rho * hl); };
-    std::vector<uint32_t> perm(nt);
-    for (int pass = 0; pass < 8; ++pass) {
-      for (size_t t = 0; t < nt; ++t) perm[t] = (uint32_t)t;
-      std::mt19937 rng(12345u + (unsigned)pass);
-      for (size_t i = nt; i > 1; --i) std::swap(perm[i - 1], perm[rng() % i]);      // own Fisher-Yates: same on every rank
-      size_t moved = 0;
-      for (uint32_t t : perm) {
-        const int a = owner_r[t];
-        const double sz = (double)plan->h_size[t];
-        const int32_t* row = TG.nbr.data() + (size_t)t * TG.deg;
-        int best_b = -1;
-        double best_new = 0, best_sum = 0, best_da = 0, best_db = 0;
-        for (int d0 = 0; d0 < TG.deg; ++d0) {
-          if (row[d0] < 0) continue;
-          const int b = owner_r[row[d0]];
-          if (b == a) continue;
-          bool seen_b = false;
-          for (int d1 = 0; d1 < d0 && !seen_b; ++d1) seen_b = row[d1] >= 0 && owner_r[row[d1]] == b;
-          if (seen_b) continue;
-          double da = 0, db = 0;
-          for (int d = 0; d < TG.deg; ++d) {
-            const int32_t n = row[d];
-            if (n < 0) continue;
-            if (cnt[a][n] == 1 && owner_r[n] != a) da -= (double)plan->h_size[n];
-            if (cnt[b][n] == 0 && owner_r[n] != b) db += (double)plan->h_size[n];
-          }
-          if (cnt[b][t] > 0) db -= sz;
-          if (cnt[a][t] > 0) da += sz;
-          const double old_v = std::max(obj(rows[a], halo[a]), obj(rows[b], halo[b]));
-          const double new_v = std::max(obj(rows[a] - sz, halo[a] + da), obj(rows[b] + sz, halo[b] + db));
-          const bool better = new_v < old_v || (new_v == old_v && da + db < 0);
-          if (better && (best_b < 0 || new_v < best_new || (new_v == best_new && da + db < best_sum))) {
-            best_b = b; best_new = new_v; best_sum = da + db; best_da = da; best_db = db;
-          }
-        }
-        if (best_b < 0) continue;
-        for (int d = 0; d < TG.deg; ++d) if (row[d] >= 0) { --cnt[a][row[d]]; ++cnt[best_b][row[d]]; }
-        owner_r[t] = best_b;
-        rows[a] -= sz; rows[best_b] += sz;
-        halo[a] += best_da; halo[best_b] += best_db;
-        ++moved;
+    std::stable_sort(ranked.begin(), ranked.end());
+    const int want = getenv("EDCUDA_SHARD_STARTS") ? std::max(1, atoi(getenv("EDCUDA_SHARD_STARTS"))) : 16;
+    const size_t n_starts = std::min<size_t>((size_t)want, ranked.size());
+    struct Start { std::vector<uint32_t> order; std::vector<int> owner; double objective = 0, halo_max = 0, halo_sum = 0; };
+    std::vector<Start> starts(n_starts);
+    auto refine = [&](Start& S, const KeySpec& K) {
+      u1_order_by_key(plan, K, S.order);
+      u1_cut(plan, S.order, world, S.owner);
+      std::vector<int>& owner_r = S.owner;
+      std::vector<std::vector<int32_t>> cnt(world, std::vector<int32_t>(nt, 0));     // cnt[r][n]: tiles of r that read n
+      std::vector<double> rows(world, 0.0), halo(world, 0.0);
+      for (size_t t = 0; t < nt; ++t) {
+        rows[owner_r[t]] += (double)plan->h_size[t];
+        const int32_t* row = TG.nbr.data() + t * TG.deg;
+        for (int d = 0; d < TG.deg; ++d) if (row[d] >= 0) ++cnt[owner_r[t]][row[d]];
       }
-      if (moved == 0) break;
+      for (int r = 0; r < world; ++r)
+        for (size_t n = 0; n < nt; ++n) if (cnt[r][n] > 0 && owner_r[n] != r) halo[r] += (double)plan->h_size[n];
+      auto obj = [&](double rw, double hl) { return std::max(rw, rho * hl); };
+      double total_rows = 0;
+      for (int r = 0; r < world; ++r) total_rows += rows[r];
+      const double row_cap = 1.25 * total_rows / world;        // no shard grows beyond +25 % whatever the halo says
+      std::vector<uint32_t> perm(nt);
+      for (int pass = 0; pass < 8; ++pass) {
+        for (size_t t = 0; t < nt; ++t) perm[t] = (uint32_t)t;
+        std::mt19937 rng(12345u + (unsigned)pass);
+        for (size_t i = nt; i > 1; --i) std::swap(perm[i - 1], perm[rng() % i]);      // own Fisher-Yates: same on every rank
+        size_t moved = 0;
+        for (uint32_t t : perm) {
+          const int a = owner_r[t];
+          const double sz = (double)plan->h_size[t];
+          const int32_t* row = TG.nbr.data() + (size_t)t * TG.deg;
+          int best_b = -1;
+          double best_new = 0, best_sum = 0, best_da = 0, best_db = 0;
+          for (int d0 = 0; d0 < TG.deg; ++d0) {
+            if (row[d0] < 0) continue;
+            const int b = owner_r[row[d0]];
+            if (b == a || rows[b] + sz > row_cap) continue;
+            bool seen_b = false;
+            for (int d1 = 0; d1 < d0 && !seen_b; ++d1) seen_b = row[d1] >= 0 && owner_r[row[d1]] == b;
+            if (seen_b) continue;
+            double da = 0, db = 0;
+            for (int d = 0; d < TG.deg; ++d) {
+              const int32_t n = row[d];
+              if (n < 0) continue;
+              if (cnt[a][n] == 1 && owner_r[n] != a) da -= (double)plan->h_size[n];
+              if (cnt[b][n] == 0 && owner_r[n] != b) db += (double)plan->h_size[n];
+            }
+            if (cnt[b][t] > 0) db -= sz;
+            if (cnt[a][t] > 0) da += sz;
+            const double old_v = std::max(obj(rows[a], halo[a]), obj(rows[b], halo[b]));
+            const double new_v = std::max(obj(rows[a] - sz, halo[a] + da), obj(rows[b] + sz, halo[b] + db));
+            const bool better = new_v < old_v || (new_v == old_v && da + db < 0);
+            if (better && (best_b < 0 || new_v < best_new || (new_v == best_new && da + db < best_sum))) {
+              best_b = b; best_new = new_v; best_sum = da + db; best_da = da; best_db = db;
+            }
+          }
+          if (best_b < 0) continue;
+          for (int d = 0; d < TG.deg; ++d) if (row[d] >= 0) { --cnt[a][row[d]]; ++cnt[best_b][row[d]]; }
+          owner_r[t] = best_b;
+          rows[a] -= sz; rows[best_b] += sz;
+          halo[a] += best_da; halo[best_b] += best_db;
+          ++moved;
+        }
+        if (moved == 0) break;
+      }
+      S.objective = S.halo_max = S.halo_sum = 0;
+      for (int r = 0; r < world; ++r) {
+        S.objective = std::max(S.objective, obj(rows[r], halo[r]));
+        S.halo_max = std::max(S.halo_max, halo[r]);
+        S.halo_sum += halo[r];
+      }
+    };
+    {
+      std::atomic<size_t> next{0};
+      auto worker = [&]() {
+        for (size_t i = next.fetch_add(1); i < n_starts; i = next.fetch_add(1)) refine(starts[i], cands[ranked[i].second]);
+      };
+      const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+      const size_t n_threads = std::min<size_t>(n_starts, std::min<unsigned>(hw, 8u));
+      std::vector<std::thread> pool;
+      for (size_t i = 1; i < n_threads; ++i) pool.emplace_back(worker);
+      worker();
+      for (auto& th : pool) th.join();
     }
-    G.key_name += " + local refinement";
+    size_t win = 0;
+    for (size_t i = 1; i < n_starts; ++i) {       // smallest objective, then largest halo, then total halo; ties stay with the better plain cut
+      const Start &A = starts[i], &B = starts[win];
+      if (A.objective < B.objective || (A.objective == B.objective && (A.halo_max < B.halo_max || (A.halo_max == B.halo_max && A.halo_sum < B.halo_sum)))) win = i;
+    }
+    G.owner = std::move(starts[win].owner);
+    best_order = std::move(starts[win].order);
+    G.key_name = cands[ranked[win].second].name + " + local refinement";
   }
   // ---- storage: every rank keeps its tiles in ascending H (fewest global row ranges); launch order = the key's order
   G.rows_of_rank.assign(world, 0);
